@@ -1,0 +1,662 @@
+// hb_api.cu -- C ABI of libhuffb200.so (see include/huffb200.h): context, launch logic, host<->device plumbing.
+// No CPU fallback: every compute entry point runs the sm_100a kernels or fails with HB_ERR_CUDA.
+#include "../../include/huffb200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "hb_decode.cuh"
+#include "hb_encode.cuh"
+#include "hb_hist.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+hb_status cuda_fail(cudaError_t e, const char *what, int line) {
+    char buf[512];
+    std::snprintf(buf, sizeof buf, "%s failed at hb_api.cu:%d: %s (%s)", what, line, cudaGetErrorName(e), cudaGetErrorString(e));
+    g_last_error = buf;
+    return HB_ERR_CUDA;
+}
+
+#define HB_CUDA(call)                                                        \
+    do {                                                                     \
+        cudaError_t e_ = (call);                                             \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call, __LINE__);        \
+    } while (0)
+#define HB_TRY(call)                                 \
+    do {                                             \
+        hb_status s_ = (call);                       \
+        if (s_ != HB_OK) return s_;                  \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;      // elements
+    hb_status reserve(size_t n) {
+        if (n <= cap) return HB_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaMalloc", __LINE__); }
+        cap = want;
+        return HB_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct DecResult {           // device -> host after the count pass
+    uint64_t total_letters;
+    uint64_t entry0;
+    uint64_t exit_last;
+    uint32_t n_dirty;
+    uint32_t pad;
+};
+
+}  // namespace
+
+struct hb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+
+    // histogram
+    unsigned long long *d_hist = nullptr;
+    int hist_grid = 0;
+    int hist_variant = 0;
+
+    // encoder
+    hb::EncTable *d_enc_table = nullptr;
+    hb_tree enc_tree_cached;
+    bool enc_tree_valid = false;
+    bool enc_wide = false;
+    DevBuf<uint64_t> enc_desc;           // [0] = ticket (low 32 bits), [1 + t] = tile descriptors
+    DevBuf<uint32_t> enc_tails;
+    unsigned long long *d_total_bits = nullptr;
+    int enc_grid_narrow = 0, enc_grid_wide = 0;
+
+    // decoder
+    hb::DecTables *d_dec_tables = nullptr;
+    hb_tree dec_tree_cached;
+    bool dec_tree_valid = false;
+    DevBuf<uint32_t> sub_info, blk_count, blk_local, dirty;
+    DevBuf<uint64_t> blk_entry, blk_exit, group_total;
+    DecResult *d_dec_result = nullptr;
+    DecResult *h_dec_result = nullptr;   // pinned
+    uint32_t *d_n_dirty = nullptr;
+    int dec_count_grid = 0, dec_write_grid = 0;
+    hb::DecParams last_dec;
+    uint64_t last_dec_total = 0;
+    bool last_dec_valid = false;
+
+    // staging for the host-buffer API
+    DevBuf<uint8_t> stage_in, stage_out;
+    uint64_t *h_hist = nullptr;          // pinned 256 x u64
+    unsigned long long *h_total_bits = nullptr;
+};
+
+namespace {
+
+hb_status check_ctx(hb_ctx *ctx) {
+    if (!ctx) return HB_ERR_INVALID_ARG;
+    HB_CUDA(cudaSetDevice(ctx->device));
+    return HB_OK;
+}
+
+bool same_codes(const hb_tree &a, const hb_tree &b) {
+    return std::memcmp(a.has_code, b.has_code, sizeof a.has_code) == 0 &&
+           std::memcmp(a.code_len, b.code_len, sizeof a.code_len) == 0 &&
+           std::memcmp(a.code, b.code, sizeof a.code) == 0;
+}
+bool same_nodes(const hb_tree &a, const hb_tree &b) {
+    return a.n_nodes == b.n_nodes && a.root == b.root &&
+           std::memcmp(a.nodes, b.nodes, sizeof(hb_node) * a.n_nodes) == 0;
+}
+
+// ---------------------------------------------------------------- histogram
+hb_status launch_hist(hb_ctx *ctx, const uint8_t *d_data, size_t n, unsigned long long *d_hist) {
+    HB_CUDA(cudaMemsetAsync(d_hist, 0, 256 * sizeof(unsigned long long), ctx->stream));
+    // per-CTA partials are u32: keep every launch below 2^32 bytes per CTA
+    const size_t max_piece = static_cast<size_t>(1) << 36;
+    for (size_t off = 0; off < n; off += max_piece) {
+        const size_t len = std::min(max_piece, n - off);
+        const size_t vecs = len / 16 + 1;
+        int grid = static_cast<int>(std::min<size_t>(ctx->hist_grid, (vecs + hb::kHistThreads - 1) / hb::kHistThreads));
+        if (grid < 1) grid = 1;
+        if (ctx->hist_variant == 1)
+            hb::hist_warp_private_kernel<<<grid, hb::kHistThreads, 0, ctx->stream>>>(d_data + off, len, d_hist);
+        else
+            hb::hist_lane_columns_kernel<<<grid, hb::kHistThreads, 0, ctx->stream>>>(d_data + off, len, d_hist);
+        ctx->launches++;
+        HB_CUDA(cudaGetLastError());
+    }
+    return HB_OK;
+}
+
+// ---------------------------------------------------------------- encoder
+hb_status upload_enc_table(hb_ctx *ctx, const hb_tree *tree) {
+    if (ctx->enc_tree_valid && same_codes(ctx->enc_tree_cached, *tree)) return HB_OK;
+    hb::EncTable t;
+    std::memset(&t, 0, sizeof t);
+    bool wide = false;
+    for (int b = 0; b < 256; b++) {
+        if (!tree->has_code[b]) continue;
+        const uint32_t len = tree->code_len[b];
+        if (len > HB_MAX_ENCODE_BITS) continue;            // rejected per input by hb_stream_bits-style checks
+        const uint64_t code = tree->code[b];
+        if (len <= 32) {
+            t.lo[b] = make_uint2(static_cast<uint32_t>(code), len);
+        } else {
+            wide = true;
+            t.lo[b] = make_uint2(static_cast<uint32_t>(code & 0xFFFFFFFFull), 32u);
+            t.hi[b] = make_uint2(static_cast<uint32_t>(code >> 32), len - 32u);
+        }
+    }
+    HB_CUDA(cudaMemcpyAsync(ctx->d_enc_table, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->enc_tree_cached = *tree;
+    ctx->enc_tree_valid = true;
+    ctx->enc_wide = wide;
+    return HB_OK;
+}
+
+hb_status launch_encode(hb_ctx *ctx, const uint8_t *d_data, size_t n, const hb_tree *tree, uint32_t start_bit,
+                        uint8_t *d_out, unsigned long long *d_total_bits) {
+    if (n == 0) {
+        if (d_total_bits) HB_CUDA(cudaMemsetAsync(d_total_bits, 0, sizeof(unsigned long long), ctx->stream));
+        return HB_OK;
+    }
+    HB_TRY(upload_enc_table(ctx, tree));
+    const size_t n_tiles = (n + hb::kEncTile - 1) / hb::kEncTile;
+    if (n_tiles > 0xFFFFFFF0ull) return HB_ERR_INVALID_ARG;
+    HB_TRY(ctx->enc_desc.reserve(n_tiles + 1));
+    HB_TRY(ctx->enc_tails.reserve(n_tiles));
+    HB_CUDA(cudaMemsetAsync(ctx->enc_desc.p, 0, (n_tiles + 1) * sizeof(uint64_t), ctx->stream));
+    hb::EncScratch sc;
+    sc.ticket = reinterpret_cast<uint32_t *>(ctx->enc_desc.p);
+    sc.desc = ctx->enc_desc.p + 1;
+    sc.tails = ctx->enc_tails.p;
+    const int max_grid = ctx->enc_wide ? ctx->enc_grid_wide : ctx->enc_grid_narrow;
+    const int grid = static_cast<int>(std::min<size_t>(max_grid, n_tiles));
+    if (ctx->enc_wide)
+        hb::encode_tiles_kernel<true><<<grid, hb::kEncThreads, 0, ctx->stream>>>(
+            d_data, n, ctx->d_enc_table, start_bit, reinterpret_cast<uint32_t *>(d_out), sc,
+            static_cast<uint32_t>(n_tiles), d_total_bits);
+    else
+        hb::encode_tiles_kernel<false><<<grid, hb::kEncThreads, 0, ctx->stream>>>(
+            d_data, n, ctx->d_enc_table, start_bit, reinterpret_cast<uint32_t *>(d_out), sc,
+            static_cast<uint32_t>(n_tiles), d_total_bits);
+    ctx->launches++;
+    HB_CUDA(cudaGetLastError());
+    return HB_OK;
+}
+
+hb_status check_encodable(const uint64_t weights[256], const hb_tree *tree, uint64_t *bits, uint8_t *missing) {
+    HB_TRY(hb_stream_bits(weights, tree, bits, missing));
+    for (int b = 0; b < 256; b++)
+        if (weights[b] && tree->code_len[b] > HB_MAX_ENCODE_BITS) return HB_ERR_CODE_TOO_LONG;
+    return HB_OK;
+}
+
+// ---------------------------------------------------------------- decoder
+void build_dec_tables(const hb_tree *tree, hb::DecTables *t) {
+    std::memset(t, 0, sizeof *t);
+    auto leaf = [&](uint32_t n) { return tree->nodes[n].left == HB_NO_CHILD; };
+    for (uint32_t i = 0; i < tree->n_nodes && i < HB_MAX_NODES; i++) {
+        const hb_node &nd = tree->nodes[i];
+        t->nodes[i] = leaf(i) ? (0xFFFFu | (static_cast<uint32_t>(nd.letter) << 16))
+                              : (static_cast<uint32_t>(nd.left) | (static_cast<uint32_t>(nd.right) << 16));
+    }
+    const uint32_t root = tree->root;
+    t->root_is_leaf = leaf(root);
+    const int K = hb::kLutBits;
+    for (uint32_t p = 0; p < (1u << K); p++) {
+        if (leaf(root)) {
+            // comp.rs:496,506-509: a lone root emits its letter for every bit
+            t->lut[p] = static_cast<uint16_t>(tree->nodes[root].letter | (1u << 8));
+            t->cnt[p] = static_cast<uint8_t>((K << 4) | K);
+            continue;
+        }
+        // first code word
+        uint32_t node = root;
+        int used = 0;
+        while (used < K && !leaf(node)) {
+            const int bit = (p >> (K - 1 - used)) & 1;
+            node = bit ? tree->nodes[node].right : tree->nodes[node].left;
+            used++;
+        }
+        t->lut[p] = leaf(node) ? static_cast<uint16_t>(tree->nodes[node].letter | (used << 8))
+                               : static_cast<uint16_t>(0x8000u | node);
+        // greedy run of complete code words inside the K bits
+        int pos = 0, letters = 0;
+        for (;;) {
+            uint32_t nd = root;
+            int q = pos;
+            while (q < K && !leaf(nd)) {
+                const int bit = (p >> (K - 1 - q)) & 1;
+                nd = bit ? tree->nodes[nd].right : tree->nodes[nd].left;
+                q++;
+            }
+            if (!leaf(nd)) break;
+            pos = q;
+            letters++;
+            if (pos >= K) break;
+        }
+        t->cnt[p] = static_cast<uint8_t>((pos << 4) | letters);
+    }
+}
+
+hb_status upload_dec_tables(hb_ctx *ctx, const hb_tree *tree) {
+    if (ctx->dec_tree_valid && same_nodes(ctx->dec_tree_cached, *tree)) return HB_OK;
+    static thread_local hb::DecTables t;
+    build_dec_tables(tree, &t);
+    HB_CUDA(cudaMemcpyAsync(ctx->d_dec_tables, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream));
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));       // `t` is reused by the next call
+    ctx->dec_tree_cached = *tree;
+    ctx->dec_tree_valid = true;
+    return HB_OK;
+}
+
+__global__ void dec_collect_kernel(hb::DecParams p, const uint64_t *grand_total, const uint32_t *n_dirty, DecResult *r) {
+    r->total_letters = *grand_total;
+    r->entry0 = p.blk_entry[0];
+    r->exit_last = p.blk_exit[p.n_blocks - 1];
+    r->n_dirty = *n_dirty;
+}
+
+hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits, uint64_t own_begin, uint64_t own_end,
+                         int64_t entry_bit, uint64_t stream_bit0, const hb_tree *tree, hb_shard_info *info) {
+    ctx->last_dec_valid = false;
+    if (reinterpret_cast<uintptr_t>(d_buf) & 3) return HB_ERR_INVALID_ARG;
+    if (own_end > avail_bits) own_end = avail_bits;
+    if (own_begin >= own_end) {
+        info->entry_bit = entry_bit;
+        info->exit_bit = own_begin;
+        info->n_letters = 0;
+        ctx->last_dec_total = 0;
+        ctx->last_dec.n_blocks = 0;
+        ctx->last_dec_valid = true;
+        return HB_OK;
+    }
+    HB_TRY(upload_dec_tables(ctx, tree));
+    const uint64_t chunk_bits = static_cast<uint64_t>(hb::kChunkWords) * 32;
+    const uint64_t first_block = own_begin / chunk_bits;
+    const uint64_t last_block = (own_end - 1) / chunk_bits;
+    const uint64_t n_blocks = last_block - first_block + 1;
+    if (n_blocks > 0x7FFFFFFFull) return HB_ERR_INVALID_ARG;
+    const uint32_t n_groups = static_cast<uint32_t>((n_blocks + hb::kScanGroup - 1) / hb::kScanGroup);
+    HB_TRY(ctx->sub_info.reserve(n_blocks * hb::kDecThreads));
+    HB_TRY(ctx->blk_count.reserve(n_blocks));
+    HB_TRY(ctx->blk_local.reserve(n_blocks));
+    HB_TRY(ctx->dirty.reserve(n_blocks));
+    HB_TRY(ctx->blk_entry.reserve(n_blocks));
+    HB_TRY(ctx->blk_exit.reserve(n_blocks));
+    HB_TRY(ctx->group_total.reserve(n_groups + 1));
+
+    hb::DecParams p;
+    p.words = reinterpret_cast<const uint32_t *>(d_buf);
+    p.n_words_readable = (avail_bits + 31) / 32;
+    p.avail_bits = avail_bits;
+    p.own_begin = own_begin;
+    p.own_end = own_end;
+    p.entry_bit = entry_bit;
+    p.stream_bit0 = stream_bit0;
+    p.len_gcd = tree->len_gcd ? tree->len_gcd : 1;
+    p.fixed_len = (tree->min_len == tree->max_len) ? tree->max_len : 0;
+    if (tree->nodes[tree->root].left == HB_NO_CHILD) { p.fixed_len = 1; p.len_gcd = 1; }
+    p.first_block = static_cast<uint32_t>(first_block);
+    p.n_blocks = static_cast<uint32_t>(n_blocks);
+    p.sub_info = ctx->sub_info.p;
+    p.blk_entry = ctx->blk_entry.p;
+    p.blk_exit = ctx->blk_exit.p;
+    p.blk_count = ctx->blk_count.p;
+
+    const int grid = static_cast<int>(std::min<uint64_t>(ctx->dec_count_grid, n_blocks));
+    hb::dec_count_kernel<<<grid, hb::kDecThreads, hb::kDecSmemCount, ctx->stream>>>(p, ctx->d_dec_tables);
+    ctx->launches++;
+    HB_CUDA(cudaGetLastError());
+
+    uint64_t *d_grand = ctx->group_total.p + n_groups;
+    for (int round = 0; round < 2; round++) {
+        HB_CUDA(cudaMemsetAsync(ctx->d_n_dirty, 0, sizeof(uint32_t), ctx->stream));
+        hb::dec_verify_kernel<<<static_cast<unsigned>((n_blocks + 255) / 256), 256, 0, ctx->stream>>>(p, ctx->dirty.p, ctx->d_n_dirty);
+        hb::dec_scan_groups_kernel<<<n_groups, hb::kDecThreads, 0, ctx->stream>>>(ctx->blk_count.p, p.n_blocks, ctx->blk_local.p, ctx->group_total.p);
+        hb::dec_scan_totals_kernel<<<1, hb::kDecThreads, 0, ctx->stream>>>(ctx->group_total.p, n_groups, d_grand);
+        dec_collect_kernel<<<1, 1, 0, ctx->stream>>>(p, d_grand, ctx->d_n_dirty, ctx->d_dec_result);
+        ctx->launches += 4;
+        HB_CUDA(cudaGetLastError());
+        HB_CUDA(cudaMemcpyAsync(ctx->h_dec_result, ctx->d_dec_result, sizeof(DecResult), cudaMemcpyDeviceToHost, ctx->stream));
+        HB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_dec_result->n_dirty == 0) break;
+        if (round == 1) { g_last_error = "decoder chain repair did not converge"; return HB_ERR_CUDA; }
+        // rare: a chunk whose speculative entry was wrong even after a 1024-bit look-back -> serial repair
+        hb::dec_fix_kernel<<<1, hb::kDecThreads, hb::kDecSmemCount, ctx->stream>>>(p, ctx->d_dec_tables, ctx->dirty.p);
+        ctx->launches++;
+        HB_CUDA(cudaGetLastError());
+    }
+    const DecResult &r = *ctx->h_dec_result;
+    info->entry_bit = r.entry0 == hb::kEnd64 ? static_cast<int64_t>(avail_bits) : static_cast<int64_t>(r.entry0);
+    info->exit_bit = r.exit_last == hb::kEnd64 ? avail_bits : r.exit_last;
+    info->n_letters = r.total_letters;
+    ctx->last_dec = p;
+    ctx->last_dec_total = r.total_letters;
+    ctx->last_dec_valid = true;
+    return HB_OK;
+}
+
+hb_status run_write_pass(hb_ctx *ctx, uint8_t *d_out, size_t out_cap) {
+    if (!ctx->last_dec_valid) return HB_ERR_INVALID_ARG;
+    if (ctx->last_dec_total > out_cap) return HB_ERR_CAPACITY;
+    if (ctx->last_dec_total == 0 || ctx->last_dec.n_blocks == 0) return HB_OK;
+    const hb::DecParams &p = ctx->last_dec;
+    const int grid = static_cast<int>(std::min<uint32_t>(ctx->dec_write_grid, p.n_blocks));
+    hb::dec_write_kernel<<<grid, hb::kDecThreads, hb::kDecSmemWrite, ctx->stream>>>(
+        p, ctx->d_dec_tables, ctx->blk_local.p, ctx->group_total.p, d_out);
+    ctx->launches++;
+    HB_CUDA(cudaGetLastError());
+    return HB_OK;
+}
+
+}  // namespace
+
+// ================================================================ C ABI
+extern "C" {
+
+const char *hb_status_str(int status) {
+    switch (status) {
+        case HB_OK: return "ok";
+        case HB_ERR_EMPTY_WEIGHTS: return "provided empty weights";
+        case HB_ERR_MISSING_LETTER: return "letter not found in codes";
+        case HB_ERR_EMPTY_COMP: return "provided comp_bytes are empty";
+        case HB_ERR_BAD_PADDING: return "padding bits cannot be larger than 7";
+        case HB_ERR_CAPACITY: return "buffer too small";
+        case HB_ERR_BIN_TOO_SMALL: return "Provided BitVec is too small for an encoded HuffTree";
+        case HB_ERR_BIN_TOO_BIG: return "Provided BitVec is too big for an encoded HuffTree";
+        case HB_ERR_BYTES_SHORT: return "slice too short";
+        case HB_ERR_TREE_LEN: return "stored tree length must be at least 2";
+        case HB_ERR_INVALID_TREE: return "invalid tree in slice";
+        case HB_ERR_CUDA: return "CUDA error";
+        case HB_ERR_INVALID_ARG: return "invalid argument";
+        case HB_ERR_CODE_TOO_LONG: return "code longer than 64 bits";
+        case HB_ERR_NO_MEM: return "out of host memory";
+        default: return "unknown status";
+    }
+}
+
+const char *hb_last_error(void) { return g_last_error.c_str(); }
+int hb_version(void) { return HB_VERSION_MAJOR * 100 + HB_VERSION_MINOR; }
+
+hb_status hb_ctx_create(int device, hb_ctx **out) {
+    if (!out) return HB_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    HB_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) { g_last_error = "no such CUDA device"; return HB_ERR_CUDA; }
+    HB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    HB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        g_last_error = std::string("libhuffb200 is built for sm_100a only; device is ") + prop.name;
+        return HB_ERR_CUDA;
+    }
+    hb_ctx *ctx = new (std::nothrow) hb_ctx();
+    if (!ctx) return HB_ERR_NO_MEM;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    const char *hv = std::getenv("HB_HIST_VARIANT");
+    ctx->hist_variant = hv ? std::atoi(hv) : 0;
+    hb_status rc = [&]() -> hb_status {
+        HB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        HB_CUDA(cudaMalloc(&ctx->d_hist, 256 * sizeof(unsigned long long)));
+        HB_CUDA(cudaMalloc(&ctx->d_enc_table, sizeof(hb::EncTable)));
+        HB_CUDA(cudaMalloc(&ctx->d_total_bits, sizeof(unsigned long long)));
+        HB_CUDA(cudaMalloc(&ctx->d_dec_tables, sizeof(hb::DecTables)));
+        HB_CUDA(cudaMalloc(&ctx->d_dec_result, sizeof(DecResult)));
+        HB_CUDA(cudaMalloc(&ctx->d_n_dirty, sizeof(uint32_t)));
+        HB_CUDA(cudaMallocHost(&ctx->h_dec_result, sizeof(DecResult)));
+        HB_CUDA(cudaMallocHost(&ctx->h_hist, 256 * sizeof(uint64_t)));
+        HB_CUDA(cudaMallocHost(&ctx->h_total_bits, sizeof(unsigned long long)));
+        HB_CUDA(cudaFuncSetAttribute(hb::dec_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::kDecSmemCount)));
+        HB_CUDA(cudaFuncSetAttribute(hb::dec_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::kDecSmemCount)));
+        HB_CUDA(cudaFuncSetAttribute(hb::dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::kDecSmemWrite)));
+        int occ = 0;
+        if (ctx->hist_variant == 1)
+            HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::hist_warp_private_kernel, hb::kHistThreads, 0));
+        else
+            HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::hist_lane_columns_kernel, hb::kHistThreads, 0));
+        ctx->hist_grid = ctx->sm_count * std::max(occ, 1);
+        HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::encode_tiles_kernel<false>, hb::kEncThreads, 0));
+        ctx->enc_grid_narrow = ctx->sm_count * std::max(occ, 1);
+        HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::encode_tiles_kernel<true>, hb::kEncThreads, 0));
+        ctx->enc_grid_wide = ctx->sm_count * std::max(occ, 1);
+        HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::dec_count_kernel, hb::kDecThreads, hb::kDecSmemCount));
+        ctx->dec_count_grid = ctx->sm_count * std::max(occ, 1);
+        HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::dec_write_kernel, hb::kDecThreads, hb::kDecSmemWrite));
+        ctx->dec_write_grid = ctx->sm_count * std::max(occ, 1);
+        return HB_OK;
+    }();
+    if (rc != HB_OK) { hb_ctx_destroy(ctx); return rc; }
+    *out = ctx;
+    return HB_OK;
+}
+
+hb_status hb_ctx_destroy(hb_ctx *ctx) {
+    if (!ctx) return HB_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_hist); cudaFree(ctx->d_enc_table); cudaFree(ctx->d_total_bits); cudaFree(ctx->d_dec_tables);
+    cudaFree(ctx->d_dec_result); cudaFree(ctx->d_n_dirty);
+    if (ctx->h_dec_result) cudaFreeHost(ctx->h_dec_result);
+    if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
+    if (ctx->h_total_bits) cudaFreeHost(ctx->h_total_bits);
+    ctx->enc_desc.release(); ctx->enc_tails.release();
+    ctx->sub_info.release(); ctx->blk_count.release(); ctx->blk_local.release(); ctx->dirty.release();
+    ctx->blk_entry.release(); ctx->blk_exit.release(); ctx->group_total.release();
+    ctx->stage_in.release(); ctx->stage_out.release();
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return HB_OK;
+}
+
+hb_status hb_ctx_sync(hb_ctx *ctx) {
+    HB_TRY(check_ctx(ctx));
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return HB_OK;
+}
+
+void *hb_ctx_stream(hb_ctx *ctx) { return ctx ? static_cast<void *>(ctx->stream) : nullptr; }
+
+hb_status hb_ctx_kernel_launches(hb_ctx *ctx, uint64_t *count) {
+    if (!ctx || !count) return HB_ERR_INVALID_ARG;
+    *count = ctx->launches;
+    return HB_OK;
+}
+
+void hb_free(void *p) { std::free(p); }
+
+hb_status hb_host_alloc(size_t bytes, void **p) {
+    if (!p) return HB_ERR_INVALID_ARG;
+    HB_CUDA(cudaMallocHost(p, bytes ? bytes : 1));
+    return HB_OK;
+}
+void hb_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---------------------------------------------------------------- device-buffer API
+hb_status hb_histogram_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, uint64_t *d_hist256) {
+    HB_TRY(check_ctx(ctx));
+    if (!d_hist256 || (n && !d_data)) return HB_ERR_INVALID_ARG;
+    return launch_hist(ctx, d_data, n, reinterpret_cast<unsigned long long *>(d_hist256));
+}
+
+hb_status hb_encode_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, const hb_tree *tree, uint32_t start_bit,
+                           uint8_t *d_out, size_t out_cap, uint64_t *d_total_bits) {
+    HB_TRY(check_ctx(ctx));
+    if (!tree || !d_out || (n && !d_data) || start_bit > 31) return HB_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_data) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 3)) return HB_ERR_INVALID_ARG;
+    (void)out_cap;   // capacity is the caller's contract (exact size comes from hb_stream_bits); checked in the *_u8 path
+    return launch_encode(ctx, d_data, n, tree, start_bit, d_out, reinterpret_cast<unsigned long long *>(d_total_bits));
+}
+
+hb_status hb_compress_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, int order_mode, hb_tree *tree_out,
+                             uint8_t *d_out, size_t out_cap, size_t *comp_len, uint8_t *padding_bits) {
+    HB_TRY(check_ctx(ctx));
+    if (!tree_out || !d_out || !comp_len || !padding_bits || (n && !d_data)) return HB_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_data) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 3)) return HB_ERR_INVALID_ARG;
+    if (n == 0) return HB_ERR_EMPTY_WEIGHTS;                      // comp.rs:354 -> tree_inner.rs:283-285
+    HB_TRY(launch_hist(ctx, d_data, n, ctx->d_hist));
+    HB_CUDA(cudaMemcpyAsync(ctx->h_hist, ctx->d_hist, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    HB_TRY(hb_tree_from_weights(ctx->h_hist, order_mode, tree_out));
+    uint64_t bits = 0;
+    uint8_t missing = 0;
+    HB_TRY(check_encodable(ctx->h_hist, tree_out, &bits, &missing));
+    const size_t need = static_cast<size_t>((bits + 7) / 8);
+    if (((need + 3) & ~static_cast<size_t>(3)) > out_cap) { *comp_len = need; return HB_ERR_CAPACITY; }
+    HB_TRY(launch_encode(ctx, d_data, n, tree_out, 0, d_out, nullptr));
+    *comp_len = need;
+    *padding_bits = static_cast<uint8_t>((8 - bits % 8) % 8);    // comp.rs:446
+    return HB_OK;
+}
+
+hb_status hb_decode_count_dev(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits, uint64_t own_begin,
+                              uint64_t own_end, uint64_t stream_bit0, const hb_tree *tree, hb_shard_info *info) {
+    HB_TRY(check_ctx(ctx));
+    if (!d_buf || !tree || !info) return HB_ERR_INVALID_ARG;
+    return run_count_pass(ctx, d_buf, avail_bits, own_begin, own_end, info->entry_bit, stream_bit0, tree, info);
+}
+
+hb_status hb_decode_write_dev(hb_ctx *ctx, uint8_t *d_out, size_t out_cap) {
+    HB_TRY(check_ctx(ctx));
+    if (!d_out && ctx->last_dec_total) return HB_ERR_INVALID_ARG;
+    return run_write_pass(ctx, d_out, out_cap);
+}
+
+hb_status hb_decompress_u8_dev(hb_ctx *ctx, const uint8_t *d_comp, size_t comp_len, uint8_t padding_bits,
+                               const hb_tree *tree, uint8_t *d_out, size_t out_cap, size_t *out_n) {
+    HB_TRY(check_ctx(ctx));
+    if (!tree || !out_n) return HB_ERR_INVALID_ARG;
+    if (comp_len == 0) return HB_ERR_EMPTY_COMP;                  // comp.rs:56-58
+    if (padding_bits > 7) return HB_ERR_BAD_PADDING;              // comp.rs:59-61
+    if (!d_comp) return HB_ERR_INVALID_ARG;
+    const uint64_t total_bits = static_cast<uint64_t>(comp_len) * 8 - padding_bits;
+    hb_shard_info info;
+    info.entry_bit = 0;
+    info.exit_bit = 0;
+    info.n_letters = 0;
+    HB_TRY(run_count_pass(ctx, d_comp, total_bits, 0, total_bits, 0, 0, tree, &info));
+    *out_n = static_cast<size_t>(info.n_letters);
+    if (info.n_letters > out_cap) return HB_ERR_CAPACITY;
+    if (info.n_letters && !d_out) return HB_ERR_INVALID_ARG;
+    return run_write_pass(ctx, d_out, out_cap);
+}
+
+// ---------------------------------------------------------------- host-buffer API
+hb_status hb_histogram_u8(hb_ctx *ctx, const uint8_t *data, size_t n, uint64_t out[256]) {
+    HB_TRY(check_ctx(ctx));
+    if (!out || (n && !data)) return HB_ERR_INVALID_ARG;
+    HB_TRY(ctx->stage_in.reserve(n + 16));
+    if (n) HB_CUDA(cudaMemcpyAsync(ctx->stage_in.p, data, n, cudaMemcpyHostToDevice, ctx->stream));
+    HB_TRY(launch_hist(ctx, ctx->stage_in.p, n, ctx->d_hist));
+    HB_CUDA(cudaMemcpyAsync(ctx->h_hist, ctx->d_hist, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(out, ctx->h_hist, 256 * sizeof(uint64_t));
+    return HB_OK;
+}
+
+static hb_status compress_host_common(hb_ctx *ctx, const uint8_t *data, size_t n, const hb_tree *tree, int order_mode,
+                                      hb_tree *tree_out, uint8_t **comp_bytes, size_t *comp_len, uint8_t *padding_bits,
+                                      uint8_t *missing) {
+    *comp_bytes = nullptr;
+    *comp_len = 0;
+    HB_TRY(ctx->stage_in.reserve(n + 16));
+    if (n) HB_CUDA(cudaMemcpyAsync(ctx->stage_in.p, data, n, cudaMemcpyHostToDevice, ctx->stream));
+    HB_TRY(launch_hist(ctx, ctx->stage_in.p, n, ctx->d_hist));
+    HB_CUDA(cudaMemcpyAsync(ctx->h_hist, ctx->d_hist, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!tree) {
+        HB_TRY(hb_tree_from_weights(ctx->h_hist, order_mode, tree_out));   // n == 0 -> HB_ERR_EMPTY_WEIGHTS
+        tree = tree_out;
+    }
+    uint64_t bits = 0;
+    uint8_t miss = 0;
+    hb_status rc = hb_stream_bits(ctx->h_hist, tree, &bits, &miss);
+    if (rc == HB_ERR_MISSING_LETTER) {
+        // comp.rs:424-432 reports the first offending letter in INPUT order: find it on the host copy
+        for (size_t i = 0; i < n; i++)
+            if (!tree->has_code[data[i]]) { miss = data[i]; break; }
+        if (missing) *missing = miss;
+        return rc;
+    }
+    HB_TRY(rc);
+    for (int b = 0; b < 256; b++)
+        if (ctx->h_hist[b] && tree->code_len[b] > HB_MAX_ENCODE_BITS) return HB_ERR_CODE_TOO_LONG;
+    if (bits == 0) return HB_ERR_EMPTY_COMP;                      // comp.rs:450 -> :56-58 (n == 0 with a given tree)
+    const size_t need = static_cast<size_t>((bits + 7) / 8);
+    HB_TRY(ctx->stage_out.reserve(need + 16));
+    HB_TRY(launch_encode(ctx, ctx->stage_in.p, n, tree, 0, ctx->stage_out.p, nullptr));
+    uint8_t *host = static_cast<uint8_t *>(std::malloc(need));
+    if (!host) return HB_ERR_NO_MEM;
+    cudaError_t e = cudaMemcpyAsync(host, ctx->stage_out.p, need, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { std::free(host); return cuda_fail(e, "D2H of the compressed stream", __LINE__); }
+    *comp_bytes = host;
+    *comp_len = need;
+    *padding_bits = static_cast<uint8_t>((8 - bits % 8) % 8);
+    return HB_OK;
+}
+
+hb_status hb_compress_u8(hb_ctx *ctx, const uint8_t *data, size_t n, int order_mode, hb_tree *tree_out,
+                         uint8_t **comp_bytes, size_t *comp_len, uint8_t *padding_bits) {
+    HB_TRY(check_ctx(ctx));
+    if (!tree_out || !comp_bytes || !comp_len || !padding_bits || (n && !data)) return HB_ERR_INVALID_ARG;
+    if (n == 0) return HB_ERR_EMPTY_WEIGHTS;
+    return compress_host_common(ctx, data, n, nullptr, order_mode, tree_out, comp_bytes, comp_len, padding_bits, nullptr);
+}
+
+hb_status hb_compress_with_tree_u8(hb_ctx *ctx, const uint8_t *data, size_t n, const hb_tree *tree,
+                                   uint8_t **comp_bytes, size_t *comp_len, uint8_t *padding_bits, uint8_t *missing) {
+    HB_TRY(check_ctx(ctx));
+    if (!tree || !comp_bytes || !comp_len || !padding_bits || (n && !data)) return HB_ERR_INVALID_ARG;
+    if (n == 0) return HB_ERR_EMPTY_COMP;                         // empty letters -> CompressData::new panics (comp.rs:56-58)
+    return compress_host_common(ctx, data, n, tree, 0, nullptr, comp_bytes, comp_len, padding_bits, missing);
+}
+
+hb_status hb_decompress_u8(hb_ctx *ctx, const uint8_t *comp, size_t comp_len, uint8_t padding_bits,
+                           const hb_tree *tree, uint8_t **out, size_t *out_n) {
+    HB_TRY(check_ctx(ctx));
+    if (!tree || !out || !out_n) return HB_ERR_INVALID_ARG;
+    *out = nullptr;
+    *out_n = 0;
+    if (comp_len == 0) return HB_ERR_EMPTY_COMP;
+    if (padding_bits > 7) return HB_ERR_BAD_PADDING;
+    if (!comp) return HB_ERR_INVALID_ARG;
+    HB_TRY(ctx->stage_in.reserve(comp_len + 16));
+    HB_CUDA(cudaMemcpyAsync(ctx->stage_in.p, comp, comp_len, cudaMemcpyHostToDevice, ctx->stream));
+    const uint64_t total_bits = static_cast<uint64_t>(comp_len) * 8 - padding_bits;
+    hb_shard_info info;
+    HB_TRY(run_count_pass(ctx, ctx->stage_in.p, total_bits, 0, total_bits, 0, 0, tree, &info));
+    const size_t n = static_cast<size_t>(info.n_letters);
+    uint8_t *host = static_cast<uint8_t *>(std::malloc(n ? n : 1));
+    if (!host) return HB_ERR_NO_MEM;
+    if (n) {
+        hb_status rc = ctx->stage_out.reserve(n + 16);
+        if (rc == HB_OK) rc = run_write_pass(ctx, ctx->stage_out.p, n);
+        if (rc != HB_OK) { std::free(host); return rc; }
+        cudaError_t e = cudaMemcpyAsync(host, ctx->stage_out.p, n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { std::free(host); return cuda_fail(e, "D2H of the decoded letters", __LINE__); }
+    }
+    *out = host;
+    *out_n = n;
+    return HB_OK;
+}
+
+}  // extern "C"

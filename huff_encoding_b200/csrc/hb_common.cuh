@@ -1,0 +1,62 @@
+// hb_common.cuh -- small device helpers shared by the sm_100a kernels of libhuffb200.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hb {
+
+constexpr int kWarp = 32;
+
+// streaming 128-bit load: read-only path, do not allocate in L1 (every input byte is touched once)
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream_u4(uint4 *p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// 64-bit flag/value words of the decoupled look-back: release store by the producer, acquire load by the consumer
+__device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t *p) {
+    uint64_t r;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_release_u64(uint64_t *p, uint64_t v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+    uint32_t r;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+}
+
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int k) { return (w >> (8 * k)) & 0xFFu; }
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t w) { return __byte_perm(w, 0, 0x0123); }
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+template <typename T>
+__device__ __forceinline__ T warp_incl_scan(T v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane_id() >= d) v += o;
+    }
+    return v;
+}
+
+}  // namespace hb

@@ -1,0 +1,128 @@
+// hb_hist.cuh -- K1: 256-bin byte histogram (replaces build_weights_map, weights.rs:116-123, and
+// ByteWeights::from_bytes, weights.rs:265-279).
+//
+// HBM-bound read of N bytes.  128-bit streaming loads; counts go to shared-memory bins that are privatised
+// per LANE rather than per warp: bin b of lane l lives at word b*32 + l, so the 32 lanes of any warp always hit
+// 32 different banks whatever the data looks like (a single-symbol input is as fast as uniform noise), and all
+// warps of the CTA share the one 32 KB table through native shared-memory atomics.  Per-CTA u32 partials are
+// folded into the global u64 bins with one atomic per non-empty bin.
+//
+// Algorithmic bytes: N read, 2 KiB written.
+#pragma once
+
+#include "hb_common.cuh"
+
+namespace hb {
+
+constexpr int kHistThreads = 512;
+constexpr int kHistUnroll = 4;            // 128-bit loads in flight per thread
+
+__device__ __forceinline__ void hist_red(uint32_t addr) {
+    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(1u) : "memory");
+}
+
+__device__ __forceinline__ void hist_word(uint32_t lane_base, uint32_t w) {
+    hist_red(lane_base + ((w & 0xFFu) << 7));
+    hist_red(lane_base + (((w >> 8) & 0xFFu) << 7));
+    hist_red(lane_base + (((w >> 16) & 0xFFu) << 7));
+    hist_red(lane_base + ((w >> 24) << 7));
+}
+
+// data: any alignment.  hist: 256 x u64, zeroed by the caller (cudaMemsetAsync) before the launch.
+__global__ void __launch_bounds__(kHistThreads)
+hist_lane_columns_kernel(const uint8_t *__restrict__ data, size_t n, unsigned long long *__restrict__ hist) {
+    __shared__ uint32_t cols[256 * 32];
+    for (int i = threadIdx.x; i < 256 * 32; i += kHistThreads) cols[i] = 0;
+    __syncthreads();
+
+    const uint32_t lane_base = static_cast<uint32_t>(__cvta_generic_to_shared(cols)) + (lane_id() << 2);
+
+    // split into unaligned head, 16-byte vectors, tail
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(data);
+    size_t head = (16 - (addr & 15)) & 15;
+    if (head > n) head = n;
+    const size_t n_vec = (n - head) / 16;
+    const size_t tail_begin = head + n_vec * 16;
+    const uint4 *vec = reinterpret_cast<const uint4 *>(data + head);
+
+    const size_t stride = static_cast<size_t>(gridDim.x) * kHistThreads;
+    size_t i = static_cast<size_t>(blockIdx.x) * kHistThreads + threadIdx.x;
+    // main loop: kHistUnroll independent loads, then the atomics
+    for (; i + (kHistUnroll - 1) * stride < n_vec; i += kHistUnroll * stride) {
+        uint4 v[kHistUnroll];
+#pragma unroll
+        for (int u = 0; u < kHistUnroll; u++) v[u] = ld_stream_u4(vec + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < kHistUnroll; u++) {
+            hist_word(lane_base, v[u].x);
+            hist_word(lane_base, v[u].y);
+            hist_word(lane_base, v[u].z);
+            hist_word(lane_base, v[u].w);
+        }
+    }
+    for (; i < n_vec; i += stride) {
+        uint4 v = ld_stream_u4(vec + i);
+        hist_word(lane_base, v.x);
+        hist_word(lane_base, v.y);
+        hist_word(lane_base, v.z);
+        hist_word(lane_base, v.w);
+    }
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < head) hist_red(lane_base + (static_cast<uint32_t>(data[threadIdx.x]) << 7));
+        const size_t n_tail = n - tail_begin;
+        if (threadIdx.x < n_tail) hist_red(lane_base + (static_cast<uint32_t>(data[tail_begin + threadIdx.x]) << 7));
+    }
+    __syncthreads();
+
+    // fold the 32 lane columns of each bin (rotated start -> conflict-free) and publish
+    if (threadIdx.x < 256) {
+        const uint32_t b = threadIdx.x;
+        uint32_t sum = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) sum += cols[b * 32 + ((j + b) & 31)];
+        if (sum) atomicAdd(hist + b, static_cast<unsigned long long>(sum));
+    }
+}
+
+// Comparison variant kept for profiling only (profiles/): classic per-warp private 256-bin histograms with data-
+// dependent bank and address conflicts.  Selected with HB_HIST_VARIANT=1.
+__global__ void __launch_bounds__(kHistThreads)
+hist_warp_private_kernel(const uint8_t *__restrict__ data, size_t n, unsigned long long *__restrict__ hist) {
+    constexpr int kWarps = kHistThreads / 32;
+    __shared__ uint32_t bins[kWarps * 256];
+    for (int i = threadIdx.x; i < kWarps * 256; i += kHistThreads) bins[i] = 0;
+    __syncthreads();
+    uint32_t *mine = bins + (threadIdx.x >> 5) * 256;
+
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(data);
+    size_t head = (16 - (addr & 15)) & 15;
+    if (head > n) head = n;
+    const size_t n_vec = (n - head) / 16;
+    const size_t tail_begin = head + n_vec * 16;
+    const uint4 *vec = reinterpret_cast<const uint4 *>(data + head);
+    const size_t stride = static_cast<size_t>(gridDim.x) * kHistThreads;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * kHistThreads + threadIdx.x; i < n_vec; i += stride) {
+        uint4 v = ld_stream_u4(vec + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            atomicAdd(mine + (w[k] & 0xFF), 1u);
+            atomicAdd(mine + ((w[k] >> 8) & 0xFF), 1u);
+            atomicAdd(mine + ((w[k] >> 16) & 0xFF), 1u);
+            atomicAdd(mine + (w[k] >> 24), 1u);
+        }
+    }
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < head) atomicAdd(mine + data[threadIdx.x], 1u);
+        const size_t n_tail = n - tail_begin;
+        if (threadIdx.x < n_tail) atomicAdd(mine + data[tail_begin + threadIdx.x], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+        uint32_t sum = 0;
+        for (int wp = 0; wp < kWarps; wp++) sum += bins[wp * 256 + threadIdx.x];
+        if (sum) atomicAdd(hist + threadIdx.x, static_cast<unsigned long long>(sum));
+    }
+}
+
+}  // namespace hb

@@ -1,0 +1,160 @@
+"""Multi-GPU path: contiguous input shards, one process per GPU, torch.distributed for the two tiny exchanges.
+
+compress:
+    local histogram kernel -> all_reduce(SUM) of the 256 bins (2 KiB) -> every rank builds the identical tree on the
+    host -> local bit total = sum(local_hist * len) -> all_gather of the G totals (8 B each) -> exclusive scan =
+    the shard's GLOBAL bit offset -> encode kernel with start_bit = offset % 8 into a buffer whose byte 0 is global
+    byte offset // 8.  Concatenating the shard buffers (OR-ing the one byte two neighbours may share) gives exactly
+    the single-GPU stream; `gather_stream` does that and the tests check it against the oracle.
+decompress:
+    (a) of shards produced by `compress`: every rank knows its first code-word start exactly (start_bit), no exchange.
+    (b) of a foreign stream cut at byte boundaries (`decompress_byte_sharded`): each rank runs the count pass with a
+        speculative entry found by self-synchronisation in its halo, ranks all_gather (entry, exit, count), any rank
+        whose entry is refuted by its left neighbour's exit re-runs with the known entry (chain converges left to
+        right), then the write pass.
+
+The engine argument is the CUDA Engine in production.  The gloo/CPU tests inject an engine with the same
+methods backed by the oracle to exercise this orchestration without a GPU; the product never does.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+class ShardedCodec:
+    def __init__(self, engine, world: int = 1, rank: int = 0, dist=None):
+        self.eng, self.world, self.rank, self.dist = engine, world, rank, dist
+        self.last_info = None
+        dev = engine.device
+        self._hist2 = torch.zeros(2, 256, dtype=torch.int64, device=dev)
+        self._bits = torch.zeros(max(world, 1), dtype=torch.int64, device=dev)
+        self._mine = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    # ------------------------------------------------------------ helpers
+    def _event(self):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(self.eng.stream)
+        return ev
+
+    # ------------------------------------------------------------ compress
+    def compress(self, data: torch.Tensor, comp_buf: torch.Tensor, marks: dict | None = None) -> dict:
+        eng, dist = self.eng, self.dist
+        if marks is not None:
+            a = self._event()
+        local = eng.histogram(data)
+        if marks is not None:
+            marks["hist"] = (a, self._event())
+        self._hist2[0].copy_(local)
+        self._hist2[1].copy_(local)
+        if self.world > 1:
+            dist.all_reduce(self._hist2[1], op=dist.ReduceOp.SUM)
+        h = self._hist2.cpu().numpy()                       # host sync: the tree needs the global histogram
+        local_w, global_w = h[0].astype(np.uint64), h[1].astype(np.uint64)
+        tree = eng.tree_from_weights(global_w)
+        lens = np.array([tree.raw.code_len[b] for b in range(256)], dtype=np.uint64)
+        my_bits = int((local_w * lens).sum())
+        if self.world > 1:
+            self._mine[0] = my_bits
+            dist.all_gather_into_tensor(self._bits, self._mine)
+            all_bits = [int(x) for x in self._bits.cpu().tolist()]
+        else:
+            all_bits = [my_bits]
+        offset = sum(all_bits[: self.rank])
+        total = sum(all_bits)
+        start_bit = offset % 8
+        comp_len = (start_bit + my_bits + 7) // 8
+        if comp_buf.numel() < ((comp_len + 3) // 4) * 4:
+            raise ValueError("comp_buf too small for this shard")
+        if marks is not None:
+            a = self._event()
+        eng.encode(data, tree, comp_buf, start_bit=start_bit)
+        if marks is not None:
+            marks["encode"] = (a, self._event())
+        info = {"tree": tree, "bits": my_bits, "bit_offset": offset, "start_bit": start_bit, "comp_len": comp_len,
+                "total_bits": total, "padding_bits": (8 - total % 8) % 8, "all_bits": all_bits}
+        self.last_info = info
+        return info
+
+    # ------------------------------------------------------------ decompress of our own shards
+    def decompress(self, comp_buf: torch.Tensor, info: dict, out_buf: torch.Tensor, marks: dict | None = None) -> int:
+        eng = self.eng
+        begin, end = info["start_bit"], info["start_bit"] + info["bits"]
+        if marks is not None:
+            a = self._event()
+        _, _, n = eng.decode_count(comp_buf, end, begin, end, info["bit_offset"] - begin, info["tree"], entry_bit=begin)
+        if marks is not None:
+            marks["dec_count"] = (a, self._event())
+        if out_buf.numel() < n:
+            raise ValueError("out_buf too small")
+        if marks is not None:
+            a = self._event()
+        eng.decode_write(out_buf)
+        if marks is not None:
+            marks["dec_write"] = (a, self._event())
+        info["n_letters"] = n
+        return n
+
+    def round_trip(self, data, comp_buf, out_buf, want_events: bool = False):
+        marks = {} if want_events else None
+        info = self.compress(data, comp_buf, marks)
+        self.decompress(comp_buf, info, out_buf, marks)
+        return marks
+
+    # ------------------------------------------------------------ concatenation (tests, and users who want one blob)
+    def gather_stream(self, comp_buf: torch.Tensor, info: dict):
+        """Rank 0 returns the whole stream (numpy u8, exactly ceil(total_bits/8) bytes) + padding_bits; others None."""
+        total_bytes = (info["total_bits"] + 7) // 8
+        mine = comp_buf[: info["comp_len"]]
+        if self.world == 1:
+            return mine.cpu().numpy().copy(), info["padding_bits"]
+        cap = max((info["all_bits"][g] + 7) // 8 + 2 for g in range(self.world))
+        send = torch.zeros(cap, dtype=torch.uint8, device=comp_buf.device)
+        send[: info["comp_len"]] = mine
+        recv = [torch.zeros(cap, dtype=torch.uint8, device=comp_buf.device) for _ in range(self.world)] \
+            if self.rank == 0 else None
+        self.dist.gather(send, recv, dst=0)
+        if self.rank != 0:
+            return None
+        out = np.zeros(total_bytes, dtype=np.uint8)
+        off = 0
+        for g in range(self.world):
+            sb = off % 8
+            ln = (sb + info["all_bits"][g] + 7) // 8
+            piece = recv[g][:ln].cpu().numpy()
+            out[off // 8: off // 8 + ln] |= piece             # the shared boundary byte is OR-merged
+            off += info["all_bits"][g]
+        return out, info["padding_bits"]
+
+    # ------------------------------------------------------------ decompress of a foreign stream cut at byte boundaries
+    def decompress_byte_sharded(self, buf: torch.Tensor, buf_byte0: int, own_byte_begin: int, own_byte_end: int,
+                                total_bits: int, tree, out_alloc):
+        """`buf` holds stream bytes [buf_byte0, ...) including a halo of >= 128 bytes on both sides of the owned
+        byte range [own_byte_begin, own_byte_end) (clipped at the stream ends).  Returns (out tensor, n_letters,
+        global letter offset of this shard)."""
+        eng, dist = self.eng, self.dist
+        bit0 = buf_byte0 * 8
+        avail = min(buf.numel() * 8, total_bits - bit0)
+        own_b = own_byte_begin * 8 - bit0
+        own_e = min(own_byte_end * 8, total_bits) - bit0
+        entry = 0 if own_byte_begin == 0 else -1
+        e, x, n = eng.decode_count(buf, avail, own_b, own_e, bit0, tree, entry_bit=entry)
+        if self.world > 1:
+            for _ in range(self.world):                     # a refuted entry can cascade at most world-1 times
+                trip = torch.tensor([e + bit0, x + bit0, n], dtype=torch.int64, device=buf.device)
+                allt = torch.zeros(self.world * 3, dtype=torch.int64, device=buf.device)
+                dist.all_gather_into_tensor(allt, trip)
+                t = allt.cpu().view(self.world, 3)
+                bad = [g for g in range(1, self.world) if int(t[g, 0]) != int(t[g - 1, 1])]
+                if not bad:
+                    break
+                if self.rank in bad:
+                    want = int(t[self.rank - 1, 1]) - bit0
+                    e, x, n = eng.decode_count(buf, avail, own_b, own_e, bit0, tree, entry_bit=want)
+            counts = [int(v) for v in t[:, 2]]
+        else:
+            counts = [n]
+        out = out_alloc(n)
+        if n:
+            eng.decode_write(out)
+        return out, n, sum(counts[: self.rank])

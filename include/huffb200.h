@@ -1,0 +1,166 @@
+/*
+ * huffb200.h -- C ABI of libhuffb200.so: the B200-native (sm_100a) implementation of huff_coding's
+ * byte-alphabet hot path.  This is the drop-in boundary a Rust `-sys` crate (or any FFI) binds; see
+ * INTEGRATION.md for the reference-side binding.  Plain pointers and sizes only, no torch types.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to /root/reference/).
+ *
+ * Conventions
+ *   - every function returns an hb_status; HB_OK == 0.  Reference panics / Err values map to status
+ *     codes (table below); nothing here calls abort().
+ *   - *_u8 functions take HOST pointers, are synchronous, and own the host<->device copies.
+ *   - *_dev functions take DEVICE pointers (cudaMalloc'ed on the ctx's device, 16-byte aligned),
+ *     run on the ctx's stream and synchronise only where the algorithm needs a host step
+ *     (tree construction, output sizing); they are what bench.py times with inputs resident in HBM.
+ *   - an hb_ctx is bound to one CUDA device and is not thread-safe: one ctx per calling thread / rank.
+ *   - there is NO CPU fallback: without a usable CUDA device hb_ctx_create fails with HB_ERR_CUDA.
+ *   - buffers returned through `uint8_t **` are allocated by the library and released with hb_free().
+ */
+#ifndef HUFFB200_H
+#define HUFFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_VERSION_MAJOR 0
+#define HB_VERSION_MINOR 1
+
+#define HB_MAX_LEAVES 257              /* 256 bytes + ByteWeights' duplicate byte-0 leaf (weights.rs:396-415) */
+#define HB_MAX_NODES  (2 * HB_MAX_LEAVES - 1)
+#define HB_NO_CHILD   0xFFFFu
+#define HB_MAX_ENCODE_BITS 64          /* longest code the GPU encoder packs (needs N > 2^44 letters to exceed) */
+
+typedef enum hb_status {
+    HB_OK                 = 0,
+    HB_ERR_EMPTY_WEIGHTS  = 1,   /* panic "provided empty weights"            tree_inner.rs:283-285 */
+    HB_ERR_MISSING_LETTER = 2,   /* Err(CompressError{missing_letter})        comp.rs:426-432 */
+    HB_ERR_EMPTY_COMP     = 3,   /* panic "provided comp_bytes are empty"     comp.rs:56-58 */
+    HB_ERR_BAD_PADDING    = 4,   /* panic "padding bits cannot be larger than 7"  comp.rs:59-61 */
+    HB_ERR_CAPACITY       = 5,   /* caller-provided buffer too small (needed size is reported) */
+    HB_ERR_BIN_TOO_SMALL  = 6,   /* FromBinError "...too small..."            tree_inner.rs:532-534,556-558 */
+    HB_ERR_BIN_TOO_BIG    = 7,   /* FromBinError "...too big..."              tree_inner.rs:586-590 */
+    HB_ERR_BYTES_SHORT    = 8,   /* CompressedDataFromBytesError              comp.rs:143,149,161 */
+    HB_ERR_TREE_LEN       = 9,   /* panic "stored tree length must be at least 2"  comp.rs:153-155 */
+    HB_ERR_INVALID_TREE   = 10,  /* CompressedDataFromBytesError "invalid tree in slice"  comp.rs:172-176 */
+    HB_ERR_CUDA           = 11,  /* CUDA runtime failure; hb_last_error() has the text */
+    HB_ERR_INVALID_ARG    = 12,
+    HB_ERR_CODE_TOO_LONG  = 13,  /* a used letter's code exceeds HB_MAX_ENCODE_BITS */
+    HB_ERR_NO_MEM         = 14
+} hb_status;
+
+/* leaf insertion order into the heap (tree/branch_heap.rs:52-58) */
+#define HB_ORDER_ASC         0   /* ascending byte value: the canonical order for compress() */
+#define HB_ORDER_BYTEWEIGHTS 1   /* ByteWeights' iterator, wrap-around quirk included (weights.rs:396-415) */
+
+/* tree/branch.rs:158-162 + tree/leaf.rs:25-29, flattened */
+typedef struct hb_node {
+    uint16_t left, right;      /* HB_NO_CHILD for a letter branch */
+    uint8_t  letter;
+    uint8_t  reserved[3];
+    uint64_t weight;           /* 0 for trees read with hb_tree_from_bin (tree_inner.rs:538,573) */
+} hb_node;
+
+/* tree/tree_inner.rs:193-196 HuffTree<u8> + its read_codes() table (tree_inner.rs:388-419) */
+typedef struct hb_tree {
+    uint32_t n_nodes;
+    uint32_t root;
+    uint32_t n_leaves;
+    uint32_t max_len;          /* longest / shortest code among letters with a code */
+    uint32_t min_len;
+    uint32_t len_gcd;          /* gcd of all code lengths (decoder speculation alignment) */
+    hb_node  nodes[HB_MAX_NODES];
+    uint8_t  has_code[256];
+    uint16_t code_len[256];
+    uint64_t code[256];        /* code bits right-aligned (first bit = most significant of the len bits); 0 if len > 64 */
+} hb_tree;
+
+typedef struct hb_ctx hb_ctx;
+
+/* ---------------------------------------------------------------- library / context */
+const char *hb_status_str(int status);
+const char *hb_last_error(void);                 /* thread-local text of the last HB_ERR_CUDA */
+int  hb_version(void);                           /* major * 100 + minor */
+hb_status hb_ctx_create(int device, hb_ctx **ctx);
+hb_status hb_ctx_destroy(hb_ctx *ctx);
+hb_status hb_ctx_sync(hb_ctx *ctx);
+void     *hb_ctx_stream(hb_ctx *ctx);            /* the cudaStream_t every *_dev call is enqueued on */
+hb_status hb_ctx_kernel_launches(hb_ctx *ctx, uint64_t *count);   /* kernels launched so far (bench.py's gpu_launches) */
+void      hb_free(void *p);                      /* frees buffers returned by *_u8 calls */
+/* pinned host staging for callers that want full PCIe speed on the *_u8 path */
+hb_status hb_host_alloc(size_t bytes, void **p);
+void      hb_host_free(void *p);
+
+/* ---------------------------------------------------------------- host-only: tree + code table
+ * replaces HuffTree::<u8>::from_weights (tree_inner.rs:281-320) over HuffBranchHeap (branch_heap.rs:18-83),
+ * reproducing std::collections::BinaryHeap's tie-breaks, and read_codes() (tree_inner.rs:388-440). */
+hb_status hb_tree_from_weights(const uint64_t weights[256], int order_mode, hb_tree *tree);
+hb_status hb_tree_from_pairs(const uint8_t *letters, const uint64_t *weights, size_t n, hb_tree *tree);
+/* HuffTree::as_bin / try_from_bin (tree_inner.rs:632-668 / 522-604); bits MSB-first, dead bits zero */
+hb_status hb_tree_as_bin(const hb_tree *tree, uint8_t *out, size_t cap_bytes, size_t *n_bits);
+hb_status hb_tree_from_bin(const uint8_t *bin, size_t n_bits, hb_tree *tree);
+/* CompressData::to_bytes / try_from_bytes (comp.rs:279-300 / 128-184) */
+hb_status hb_to_bytes(const uint8_t *comp, size_t comp_len, uint8_t padding_bits, const hb_tree *tree,
+                      uint8_t *out, size_t cap, size_t *out_len);
+hb_status hb_try_from_bytes(const uint8_t *bytes, size_t n, hb_tree *tree,
+                            size_t *data_off, size_t *data_len, uint8_t *padding_bits);
+
+/* ---------------------------------------------------------------- host-buffer API (synchronous) */
+/* build_weights_map(&[u8]) (weights.rs:82-84,116-123) / ByteWeights::from_bytes (weights.rs:265-279) */
+hb_status hb_histogram_u8(hb_ctx *ctx, const uint8_t *data, size_t n, uint64_t out[256]);
+/* compress(&[u8]) (comp.rs:353-356): histogram + tree (order_mode) + encode.  n == 0 -> HB_ERR_EMPTY_WEIGHTS. */
+hb_status hb_compress_u8(hb_ctx *ctx, const uint8_t *data, size_t n, int order_mode, hb_tree *tree_out,
+                         uint8_t **comp_bytes, size_t *comp_len, uint8_t *padding_bits);
+/* compress_with_tree(&[u8], HuffTree<u8>) (comp.rs:419-451).  HB_ERR_MISSING_LETTER sets *missing to the
+ * first letter (in input order) the tree has no code for. */
+hb_status hb_compress_with_tree_u8(hb_ctx *ctx, const uint8_t *data, size_t n, const hb_tree *tree,
+                                   uint8_t **comp_bytes, size_t *comp_len, uint8_t *padding_bits, uint8_t *missing);
+/* decompress(&CompressData<u8>) (comp.rs:487-519).  comp_len == 0 -> HB_ERR_EMPTY_COMP, padding > 7 ->
+ * HB_ERR_BAD_PADDING (the CompressData::new invariants, comp.rs:55-61). */
+hb_status hb_decompress_u8(hb_ctx *ctx, const uint8_t *comp, size_t comp_len, uint8_t padding_bits,
+                           const hb_tree *tree, uint8_t **out, size_t *out_n);
+
+/* ---------------------------------------------------------------- device-buffer API (ctx stream) */
+/* d_hist256: 256 x u64 on the device; overwritten.  No host sync. */
+hb_status hb_histogram_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, uint64_t *d_hist256);
+/* Exact stream size for (histogram, tree): sum w[b] * len[b].  Host arithmetic. */
+hb_status hb_stream_bits(const uint64_t weights[256], const hb_tree *tree, uint64_t *bits, uint8_t *missing);
+/* Encoder proper = compress_with_tree's packing loop (comp.rs:422-447).  Writes the stream as if it started at
+ * bit `start_bit` (0..31) of d_out[0]: the first start_bit bits are left 0 so a neighbouring shard can be OR-ed in
+ * (multi-GPU concatenation).  d_out must hold out_cap >= ceil((start_bit + bits)/8) rounded up to 4 bytes.
+ * d_total_bits (device u64, optional) receives the number of code bits written.  Letters without a code emit
+ * nothing (callers check with hb_stream_bits first).  No host sync. */
+hb_status hb_encode_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, const hb_tree *tree, uint32_t start_bit,
+                           uint8_t *d_out, size_t out_cap, uint64_t *d_total_bits);
+/* compress() on device buffers: histogram -> (sync) host tree -> encode.  *comp_len / *padding_bits are exact. */
+hb_status hb_compress_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, int order_mode, hb_tree *tree_out,
+                             uint8_t *d_out, size_t out_cap, size_t *comp_len, uint8_t *padding_bits);
+/* decompress() on device buffers.  Decodes the bits [first_bit, total_bits) of d_comp where
+ * total_bits = 8 * comp_len - padding_bits; d_comp must be readable up to comp_len rounded up to 16 bytes.
+ * If out_cap is too small returns HB_ERR_CAPACITY with *out_n = needed letters (nothing written). */
+hb_status hb_decompress_u8_dev(hb_ctx *ctx, const uint8_t *d_comp, size_t comp_len, uint8_t padding_bits,
+                               const hb_tree *tree, uint8_t *d_out, size_t out_cap, size_t *out_n);
+
+/* ---------------------------------------------------------------- sharded decode building blocks (multi-GPU)
+ * A rank owning stream bits [own_begin, own_end) of a buffer that also holds a halo on both sides
+ * (buffer bit 0 .. avail_bits) runs the count phase with entry_bit < 0 (speculative: entry found by
+ * self-synchronisation from the halo) or with a known entry; it reports where its last code word ends
+ * (*exit_bit, relative to the buffer) and how many letters start in its range.  stream_bit0 is the position of
+ * buffer bit 0 in the whole stream (it fixes the phase for code sets whose lengths share a factor). */
+typedef struct hb_shard_info {
+    int64_t  entry_bit;     /* in: >= 0 known first code-word start, < 0 speculative.  out: entry used */
+    uint64_t exit_bit;      /* out: first code-word start >= own_end (may be > avail_bits at the stream end) */
+    uint64_t n_letters;     /* out: letters whose code word starts in [entry, own_end) and ends <= avail_bits */
+} hb_shard_info;
+hb_status hb_decode_count_dev(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits, uint64_t own_begin,
+                              uint64_t own_end, uint64_t stream_bit0, const hb_tree *tree, hb_shard_info *info);
+/* writes the letters counted by the matching hb_decode_count_dev call (same ctx, same arguments) */
+hb_status hb_decode_write_dev(hb_ctx *ctx, uint8_t *d_out, size_t out_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HUFFB200_H */

@@ -211,7 +211,8 @@ __device__ void dec_count_block(const DecParams &p, uint32_t blk, uint64_t entry
     // ---- phase B + in-CTA verification to a fixed point
     uint32_t count = 0, exitq = kEnd32;
     bool redo = active;
-    for (;;) {
+    for (int round = 0;; round++) {
+        if (round > kDecThreads + 1) asm volatile("trap;");   // cannot happen: thread t is final after t rounds
         if (redo) {
             exitq = dec_run(win, s_lut, s_cnt, s_nodes, entry, q_hi, q_avail, count);
             if (entry != kEnd32 && entry >= q_hi) { exitq = entry; count = 0; }

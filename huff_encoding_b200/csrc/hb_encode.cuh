@@ -164,7 +164,11 @@ encode_tiles_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable *
                     const long long idx = look - lane;
                     unsigned long long d = kDescPrefix;            // virtual "prefix 0" before tile 0 (never the nearest)
                     if (idx >= 0) {
-                        do { d = ld_acquire_u64(scratch.desc + idx); } while ((d >> 62) == 0);
+                        uint32_t polls = 0;
+                        do {
+                            d = ld_acquire_u64(scratch.desc + idx);
+                            if (++polls == (1u << 26)) asm volatile("trap;");   // a lost descriptor must not hang the GPU
+                        } while ((d >> 62) == 0);
                     }
                     const unsigned pm = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2);
                     const int first_prefix = pm ? __ffs(pm) - 1 : 32;

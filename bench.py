@@ -50,7 +50,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -182,15 +182,17 @@ def run_ours(args):
         return marks
 
     with torch.cuda.stream(stream):
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        time.sleep(0.3)                      # let nvidia-smi come up; its samples then cover warm-up + timed region
         for _ in range(args.warmup):
             step(False)
         stream.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        sampler.samples.clear()              # keep only samples taken during the timed region
         launches0 = eng.kernel_launches()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         all_marks = []
         ev0.record(stream)
@@ -295,7 +297,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="uniform", choices=["uniform", "zipf", "english"])

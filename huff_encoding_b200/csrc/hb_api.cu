@@ -78,11 +78,10 @@ struct hb_ctx {
     hb::EncTable *d_enc_table = nullptr;
     hb_tree enc_tree_cached;
     bool enc_tree_valid = false;
-    bool enc_wide = false;
-    DevBuf<uint64_t> enc_desc;           // [0] = ticket (low 32 bits), [1 + t] = tile descriptors
-    DevBuf<uint32_t> enc_tails;
+    int enc_chunk = 4;                   // letters per chunk: 4 (codes <= 16 bits), 2 (<= 32), 1 (<= 64)
+    DevBuf<uint64_t> enc_desc;           // one look-back descriptor per tile
     unsigned long long *d_total_bits = nullptr;
-    int enc_grid_narrow = 0, enc_grid_wide = 0;
+    int enc_grid = 0;                    // co-resident CTAs (cooperative launch)
 
     // decoder
     hb::DecTables *d_dec_tables = nullptr;
@@ -147,24 +146,42 @@ hb_status upload_enc_table(hb_ctx *ctx, const hb_tree *tree) {
     if (ctx->enc_tree_valid && same_codes(ctx->enc_tree_cached, *tree)) return HB_OK;
     hb::EncTable t;
     std::memset(&t, 0, sizeof t);
-    bool wide = false;
+    uint32_t max_len = 0;
     for (int b = 0; b < 256; b++) {
         if (!tree->has_code[b]) continue;
         const uint32_t len = tree->code_len[b];
-        if (len > HB_MAX_ENCODE_BITS) continue;            // rejected per input by hb_stream_bits-style checks
+        if (len > HB_MAX_ENCODE_BITS) continue;            // such letters are rejected per input (check_encodable)
         const uint64_t code = tree->code[b];
-        if (len <= 32) {
-            t.lo[b] = make_uint2(static_cast<uint32_t>(code), len);
-        } else {
-            wide = true;
-            t.lo[b] = make_uint2(static_cast<uint32_t>(code & 0xFFFFFFFFull), 32u);
-            t.hi[b] = make_uint2(static_cast<uint32_t>(code >> 32), len - 32u);
-        }
+        t.lo[b] = make_uint2(static_cast<uint32_t>(code & 0xFFFFFFFFull), len);
+        t.hi[b] = static_cast<uint32_t>(code >> 32);
+        max_len = std::max(max_len, len);
     }
     HB_CUDA(cudaMemcpyAsync(ctx->d_enc_table, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream));
     ctx->enc_tree_cached = *tree;
     ctx->enc_tree_valid = true;
-    ctx->enc_wide = wide;
+    ctx->enc_chunk = max_len <= 16 ? 4 : (max_len <= 32 ? 2 : 1);
+    return HB_OK;
+}
+
+template <int S>
+hb_status launch_encode_s(hb_ctx *ctx, const uint8_t *d_data, size_t n, uint32_t start_bit, uint8_t *d_out,
+                          unsigned long long *d_total_bits) {
+    const size_t tile = static_cast<size_t>(32) * hb::kEncRounds * S;
+    const size_t n_tiles = (n + tile - 1) / tile;
+    if (n_tiles > 0xFFFFFFF0ull) return HB_ERR_INVALID_ARG;
+    HB_TRY(ctx->enc_desc.reserve(n_tiles));
+    HB_CUDA(cudaMemsetAsync(ctx->enc_desc.p, 0, n_tiles * sizeof(uint64_t), ctx->stream));
+    const size_t ctas_needed = (n_tiles + hb::kEncWarps - 1) / hb::kEncWarps;
+    const int grid = static_cast<int>(std::min<size_t>(ctx->enc_grid, ctas_needed));
+    const hb::EncTable *table = ctx->d_enc_table;
+    uint32_t *out32 = reinterpret_cast<uint32_t *>(d_out);
+    uint64_t *desc = ctx->enc_desc.p;
+    uint32_t nt = static_cast<uint32_t>(n_tiles);
+    void *args[] = {&d_data, &n, &table, &start_bit, &out32, &desc, &nt, &d_total_bits};
+    // cooperative launch = all CTAs co-resident, which the tile look-back relies on
+    HB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(hb::encode_warp_tiles_kernel<S>), dim3(grid),
+                                        dim3(hb::kEncThreads), args, hb::enc_smem_bytes(S), ctx->stream));
+    ctx->launches++;
     return HB_OK;
 }
 
@@ -175,28 +192,11 @@ hb_status launch_encode(hb_ctx *ctx, const uint8_t *d_data, size_t n, const hb_t
         return HB_OK;
     }
     HB_TRY(upload_enc_table(ctx, tree));
-    const size_t n_tiles = (n + hb::kEncTile - 1) / hb::kEncTile;
-    if (n_tiles > 0xFFFFFFF0ull) return HB_ERR_INVALID_ARG;
-    HB_TRY(ctx->enc_desc.reserve(n_tiles + 1));
-    HB_TRY(ctx->enc_tails.reserve(n_tiles));
-    HB_CUDA(cudaMemsetAsync(ctx->enc_desc.p, 0, (n_tiles + 1) * sizeof(uint64_t), ctx->stream));
-    hb::EncScratch sc;
-    sc.ticket = reinterpret_cast<uint32_t *>(ctx->enc_desc.p);
-    sc.desc = ctx->enc_desc.p + 1;
-    sc.tails = ctx->enc_tails.p;
-    const int max_grid = ctx->enc_wide ? ctx->enc_grid_wide : ctx->enc_grid_narrow;
-    const int grid = static_cast<int>(std::min<size_t>(max_grid, n_tiles));
-    if (ctx->enc_wide)
-        hb::encode_tiles_kernel<true><<<grid, hb::kEncThreads, 0, ctx->stream>>>(
-            d_data, n, ctx->d_enc_table, start_bit, reinterpret_cast<uint32_t *>(d_out), sc,
-            static_cast<uint32_t>(n_tiles), d_total_bits);
-    else
-        hb::encode_tiles_kernel<false><<<grid, hb::kEncThreads, 0, ctx->stream>>>(
-            d_data, n, ctx->d_enc_table, start_bit, reinterpret_cast<uint32_t *>(d_out), sc,
-            static_cast<uint32_t>(n_tiles), d_total_bits);
-    ctx->launches++;
-    HB_CUDA(cudaGetLastError());
-    return HB_OK;
+    switch (ctx->enc_chunk) {
+        case 4: return launch_encode_s<4>(ctx, d_data, n, start_bit, d_out, d_total_bits);
+        case 2: return launch_encode_s<2>(ctx, d_data, n, start_bit, d_out, d_total_bits);
+        default: return launch_encode_s<1>(ctx, d_data, n, start_bit, d_out, d_total_bits);
+    }
 }
 
 hb_status check_encodable(const uint64_t weights[256], const hb_tree *tree, uint64_t *bits, uint8_t *missing) {
@@ -223,6 +223,7 @@ void build_dec_tables(const hb_tree *tree, hb::DecTables *t) {
             // comp.rs:496,506-509: a lone root emits its letter for every bit
             t->lut[p] = static_cast<uint16_t>(tree->nodes[root].letter | (1u << 8));
             t->cnt[p] = static_cast<uint8_t>((K << 4) | K);
+            t->lut2[p] = tree->nodes[root].letter | (static_cast<uint32_t>(tree->nodes[root].letter) << 8) | (1u << 16) | (2u << 24);
             continue;
         }
         // first code word
@@ -251,6 +252,19 @@ void build_dec_tables(const hb_tree *tree, hb::DecTables *t) {
             if (pos >= K) break;
         }
         t->cnt[p] = static_cast<uint8_t>((pos << 4) | letters);
+        // write-pass entry: up to two letters
+        if (!leaf(node)) { t->lut2[p] = 0; continue; }
+        const uint32_t len0 = static_cast<uint32_t>(used);
+        uint32_t e = tree->nodes[node].letter | (len0 << 16);
+        uint32_t nd2 = root;
+        int q2 = used;
+        while (q2 < K && !leaf(nd2)) {
+            const int bit = (p >> (K - 1 - q2)) & 1;
+            nd2 = bit ? tree->nodes[nd2].right : tree->nodes[nd2].left;
+            q2++;
+        }
+        if (leaf(nd2) && q2 > used) e |= (static_cast<uint32_t>(tree->nodes[nd2].letter) << 8) | (static_cast<uint32_t>(q2) << 24);
+        t->lut2[p] = e;
     }
 }
 
@@ -433,10 +447,15 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
         else
             HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::hist_lane_columns_kernel, hb::kHistThreads, 0));
         ctx->hist_grid = ctx->sm_count * std::max(occ, 1);
-        HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::encode_tiles_kernel<false>, hb::kEncThreads, 0));
-        ctx->enc_grid_narrow = ctx->sm_count * std::max(occ, 1);
-        HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::encode_tiles_kernel<true>, hb::kEncThreads, 0));
-        ctx->enc_grid_wide = ctx->sm_count * std::max(occ, 1);
+        HB_CUDA(cudaFuncSetAttribute(hb::encode_warp_tiles_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::enc_smem_bytes(4))));
+        HB_CUDA(cudaFuncSetAttribute(hb::encode_warp_tiles_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::enc_smem_bytes(2))));
+        HB_CUDA(cudaFuncSetAttribute(hb::encode_warp_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::enc_smem_bytes(1))));
+        HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::encode_warp_tiles_kernel<1>, hb::kEncThreads, hb::enc_smem_bytes(1)));
+        if (occ < 1) { g_last_error = "encode kernel does not fit on an SM"; return HB_ERR_CUDA; }
+        ctx->enc_grid = ctx->sm_count;                            // one persistent CTA per SM
+        int coop = 0;
+        HB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+        if (!coop) { g_last_error = "device lacks cooperative launch"; return HB_ERR_CUDA; }
         HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::dec_count_kernel, hb::kDecThreads, hb::kDecSmemCount));
         ctx->dec_count_grid = ctx->sm_count * std::max(occ, 1);
         HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::dec_write_kernel, hb::kDecThreads, hb::kDecSmemWrite));
@@ -457,7 +476,7 @@ hb_status hb_ctx_destroy(hb_ctx *ctx) {
     if (ctx->h_dec_result) cudaFreeHost(ctx->h_dec_result);
     if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
     if (ctx->h_total_bits) cudaFreeHost(ctx->h_total_bits);
-    ctx->enc_desc.release(); ctx->enc_tails.release();
+    ctx->enc_desc.release();
     ctx->sub_info.release(); ctx->blk_count.release(); ctx->blk_local.release(); ctx->dirty.release();
     ctx->blk_entry.release(); ctx->blk_exit.release(); ctx->group_total.release();
     ctx->stage_in.release(); ctx->stage_out.release();

@@ -45,7 +45,7 @@ constexpr int kLutBits = 12;
 constexpr uint32_t kEnd32 = 0xFFFFFFFFu;
 constexpr uint64_t kEnd64 = ~0ull;
 constexpr int kLookbackBits = 512;                             // in-CTA look-back window W (thread 0 uses the full halo)
-constexpr int kOutWindow = 16384;                              // letters staged per copy-out round in the write pass
+constexpr int kOutWindow = 49152;                              // letters staged per copy-out round in the write pass
 constexpr int kScanGroup = 1024;                               // CTAs per offset-scan group
 
 struct DecTables {                     // device resident, built on the host from the hb_tree
@@ -53,6 +53,8 @@ struct DecTables {                     // device resident, built on the host fro
     uint8_t  cnt[1 << kLutBits];       // (bits consumed << 4) | letters completed, 0 if the first code is longer than 12
     uint32_t nodes[HB_MAX_NODES];      // left | right << 16 ; leaf: left = 0xFFFF, right = letter
     uint32_t root_is_leaf;
+    uint32_t lut2[1 << kLutBits];      // write pass: letter0 | letter1 << 8 | len0 << 16 | len(0+1) << 24 (0 = no 2nd);
+                                       // len0 == 0: first code longer than 12 bits (slow path)
 };
 
 struct DecParams {
@@ -102,6 +104,30 @@ __device__ __forceinline__ uint32_t dec_one(const uint32_t *win, const uint16_t 
     return (q + len <= q_avail) ? len : 0;
 }
 
+// Register bit window over the staged stream: buf holds the next `have` bits, MSB first.
+struct BitReader {
+    const uint32_t *win;
+    unsigned long long buf;
+    uint32_t have, wi, q;
+    __device__ __forceinline__ void init(const uint32_t *w, uint32_t q0) {
+        win = w; q = q0; wi = q0 >> 5;
+        const uint32_t s = q0 & 31;
+        const unsigned long long two = (static_cast<unsigned long long>(win[win_phys(wi)]) << 32) | win[win_phys(wi + 1)];
+        buf = two << s;
+        have = 64 - s;
+        wi += 2;
+    }
+    __device__ __forceinline__ void refill() {          // afterwards have >= 33
+        if (have <= 32) {
+            buf |= static_cast<unsigned long long>(win[win_phys(wi)]) << (32 - have);
+            have += 32;
+            wi++;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek() const { return static_cast<uint32_t>(buf >> (64 - kLutBits)); }
+    __device__ __forceinline__ void skip(uint32_t l) { buf <<= l; have -= l; q += l; }
+};
+
 // Advance from q over whole code words while q < q_stop; count them.  Returns the first code-word start >= q_stop,
 // or kEnd32 when a code word does not fit below q_avail.
 __device__ __forceinline__ uint32_t dec_run(const uint32_t *win, const uint16_t *lut, const uint8_t *cnt_lut,
@@ -110,18 +136,24 @@ __device__ __forceinline__ uint32_t dec_run(const uint32_t *win, const uint16_t 
     uint32_t n = 0;
     if (q == kEnd32) { count = 0; return kEnd32; }
     const uint32_t fast_stop = min(q_stop, q_avail);
-    while (q + kLutBits <= fast_stop) {
-        const uint32_t c = cnt_lut[win_peek32(win, q) >> (32 - kLutBits)];
-        if (c) {
-            q += c >> 4;
-            n += c & 15u;
-        } else {
-            uint32_t letter;
-            const uint32_t len = dec_one(win, lut, nodes, q, q_avail, letter);
-            if (!len) { count = n; return kEnd32; }
-            q += len;
-            n++;
+    if (q + kLutBits <= fast_stop) {
+        BitReader rd;
+        rd.init(win, q);
+        while (rd.q + kLutBits <= fast_stop) {
+            rd.refill();
+            const uint32_t c = cnt_lut[rd.peek()];
+            if (c) {
+                rd.skip(c >> 4);
+                n += c & 15u;
+            } else {                                        // first code longer than 12 bits: tree walk, then re-prime
+                uint32_t letter;
+                const uint32_t len = dec_one(win, lut, nodes, rd.q, q_avail, letter);
+                if (!len) { count = n; return kEnd32; }
+                n++;
+                rd.init(win, rd.q + len);
+            }
         }
+        q = rd.q;
     }
     while (q < q_stop) {
         uint32_t letter;
@@ -135,7 +167,9 @@ __device__ __forceinline__ uint32_t dec_run(const uint32_t *win, const uint16_t 
 }
 
 __device__ __forceinline__ void dec_load_tables(const DecTables *__restrict__ t, uint16_t *s_lut, uint8_t *s_cnt,
-                                                uint32_t *s_nodes) {
+                                                uint32_t *s_nodes, uint32_t *s_lut2 = nullptr) {
+    if (s_lut2)
+        for (int i = threadIdx.x; i < (1 << kLutBits); i += blockDim.x) s_lut2[i] = t->lut2[i];
     const uint32_t *src_lut = reinterpret_cast<const uint32_t *>(t->lut);
     uint32_t *dst_lut = reinterpret_cast<uint32_t *>(s_lut);
     for (int i = threadIdx.x; i < (1 << kLutBits) / 2; i += blockDim.x) dst_lut[i] = src_lut[i];
@@ -254,27 +288,27 @@ __device__ void dec_count_block(const DecParams &p, uint32_t blk, uint64_t entry
 extern __shared__ __align__(16) uint8_t dec_smem[];
 
 struct DecSmem {
-    uint32_t *win; uint16_t *lut; uint8_t *cnt; uint32_t *nodes; uint32_t *exit; uint32_t *red; uint8_t *stage;
+    uint32_t *win; uint16_t *lut; uint8_t *cnt; uint32_t *nodes; uint32_t *exit; uint32_t *red; uint32_t *lut2; uint32_t *stage;
 };
 constexpr size_t dec_align16(size_t x) { return (x + 15) & ~static_cast<size_t>(15); }
 constexpr size_t kDecOffLut = dec_align16(kWinPhys * 4);
-constexpr size_t kDecOffCnt = kDecOffLut + (1 << kLutBits) * 2;
-constexpr size_t kDecOffNodes = kDecOffCnt + (1 << kLutBits);
-constexpr size_t kDecOffExit = kDecOffNodes + dec_align16(HB_MAX_NODES * 4);
-constexpr size_t kDecOffRed = kDecOffExit + kDecThreads * 4;
-constexpr size_t kDecOffStage = kDecOffRed + 64;
-constexpr size_t kDecSmemCount = kDecOffStage;
-constexpr size_t kDecSmemWrite = kDecOffStage + kOutWindow + 32;
+constexpr size_t kDecOffNodes = kDecOffLut + (1 << kLutBits) * 2;
+constexpr size_t kDecOffRed = kDecOffNodes + dec_align16(HB_MAX_NODES * 4);
+constexpr size_t kDecOffVar = kDecOffRed + 64;                       // count: cnt + exit ; write: lut2 + stage
+constexpr size_t kDecSmemCount = kDecOffVar + (1 << kLutBits) + kDecThreads * 4;
+constexpr int kStageWords = kOutWindow / 4 + 32;                     // + slack for the 4-byte alignment shift, XOR-swizzled rows
+constexpr size_t kDecSmemWrite = kDecOffVar + (1 << kLutBits) * 4 + kStageWords * 4;
 
 __device__ __forceinline__ DecSmem dec_carve(uint8_t *base) {
     DecSmem s;
     s.win = reinterpret_cast<uint32_t *>(base);
     s.lut = reinterpret_cast<uint16_t *>(base + kDecOffLut);
-    s.cnt = base + kDecOffCnt;
     s.nodes = reinterpret_cast<uint32_t *>(base + kDecOffNodes);
-    s.exit = reinterpret_cast<uint32_t *>(base + kDecOffExit);
     s.red = reinterpret_cast<uint32_t *>(base + kDecOffRed);
-    s.stage = base + kDecOffStage;
+    s.cnt = base + kDecOffVar;
+    s.exit = reinterpret_cast<uint32_t *>(base + kDecOffVar + (1 << kLutBits));
+    s.lut2 = reinterpret_cast<uint32_t *>(base + kDecOffVar);
+    s.stage = reinterpret_cast<uint32_t *>(base + kDecOffVar + (1 << kLutBits) * 4);
     return s;
 }
 
@@ -380,12 +414,19 @@ dec_scan_totals_kernel(uint64_t *group_total, uint32_t n_groups, uint64_t *grand
 }
 
 // ---- write pass
+// staging bytes live in 32-bit words whose index is XOR-swizzled by its row, so that lanes writing at a stride of a
+// multiple of 128 bytes (uniform data: 128 letters per thread) still hit 32 different banks
+__device__ __forceinline__ uint32_t stage_word(uint32_t w) { return w ^ ((w >> 5) & 31u); }
+__device__ __forceinline__ void stage_put(uint32_t *stage, uint32_t a, uint32_t letter) {
+    reinterpret_cast<uint8_t *>(stage)[(stage_word(a >> 2) << 2) | (a & 3u)] = static_cast<uint8_t>(letter);
+}
+
 __global__ void __launch_bounds__(kDecThreads)
 dec_write_kernel(DecParams p, const DecTables *__restrict__ tables, const uint32_t *__restrict__ blk_local,
                  const uint64_t *__restrict__ group_off, uint8_t *__restrict__ out) {
     DecSmem s = dec_carve(dec_smem);
     __shared__ uint32_t s_w[kDecThreads / 32];
-    dec_load_tables(tables, s.lut, nullptr, s.nodes);
+    dec_load_tables(tables, s.lut, nullptr, s.nodes, s.lut2);
     const int t = threadIdx.x;
     for (uint32_t blk = blockIdx.x; blk < p.n_blocks; blk += gridDim.x) {
         __syncthreads();
@@ -398,7 +439,6 @@ dec_write_kernel(DecParams p, const DecTables *__restrict__ tables, const uint32
         const long long win_bit0 = (static_cast<long long>(chunk) * kChunkWords - kHaloWords) * 32;
         const long long q_av = static_cast<long long>(p.avail_bits) - win_bit0;
         const uint32_t q_avail = q_av < 0 ? 0u : (q_av > static_cast<long long>(kWinBits) ? kWinBits : static_cast<uint32_t>(q_av));
-        uint32_t q = (kHaloWords + t * kSubWords) * 32u + entry_rel;
 
         // CTA-wide exclusive scan of letter counts
         const uint32_t incl = warp_incl_scan(my_count);
@@ -409,29 +449,51 @@ dec_write_kernel(DecParams p, const DecTables *__restrict__ tables, const uint32
         const uint32_t my_off = before + incl - my_count;
         const uint64_t out_base = group_off[blk / kScanGroup] + blk_local[blk];
 
+        BitReader rd;
+        if (my_count) rd.init(s.win, (kHaloWords + t * kSubWords) * 32u + entry_rel);
         uint32_t produced = 0;
         for (uint32_t win_start = 0; win_start < total; win_start += kOutWindow) {
             const uint32_t win_len = min(static_cast<uint32_t>(kOutWindow), total - win_start);
             uint8_t *dst = out + out_base + win_start;
-            const uint32_t shift = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst) & 15);   // align stage to dst
-            // decode my letters that fall into [win_start, win_start + win_len)
-            while (produced < my_count && my_off + produced < win_start + win_len) {
-                uint32_t letter = 0;
-                const uint32_t len = dec_one(s.win, s.lut, s.nodes, q, q_avail, letter);
-                q += len;
-                s.stage[shift + my_off + produced - win_start] = static_cast<uint8_t>(letter);
-                produced++;
+            const uint32_t shift = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst) & 3);   // word-align stage to dst
+            // my letters that fall into [win_start, win_start + win_len)
+            uint32_t limit = min(my_count, win_start + win_len > my_off ? win_start + win_len - my_off : 0u);
+            uint32_t a = shift + my_off + produced - win_start;                                  // staging byte address
+            while (produced < limit) {
+                rd.refill();
+                const uint32_t e = s.lut2[rd.peek()];
+                const uint32_t len0 = (e >> 16) & 0xFFu;
+                if (len0) {
+                    const uint32_t len01 = e >> 24;
+                    stage_put(s.stage, a, e & 0xFFu);
+                    if (len01 && produced + 1 < limit) {
+                        stage_put(s.stage, a + 1, (e >> 8) & 0xFFu);
+                        rd.skip(len01);
+                        produced += 2; a += 2;
+                    } else {
+                        rd.skip(len0);
+                        produced += 1; a += 1;
+                    }
+                } else {                                                                          // code longer than 12 bits
+                    uint32_t letter = 0;
+                    const uint32_t len = dec_one(s.win, s.lut, s.nodes, rd.q, q_avail, letter);
+                    stage_put(s.stage, a, letter);
+                    produced += 1; a += 1;
+                    rd.init(s.win, rd.q + len);
+                }
             }
             __syncthreads();
-            // copy out: 16-byte vectors where whole, bytes at the ragged ends
-            const uint32_t n_vec = (shift + win_len + 15) / 16;
+            // copy out whole 32-bit words; the ragged first / last word byte by byte
+            const uint32_t n_words = (shift + win_len + 3) / 4;
             uint8_t *dst_al = dst - shift;
-            for (uint32_t v = t; v < n_vec; v += kDecThreads) {
-                const uint32_t lo = v * 16, hi = lo + 16;
+            for (uint32_t w = t; w < n_words; w += kDecThreads) {
+                const uint32_t v = s.stage[stage_word(w)];
+                const uint32_t lo = w * 4, hi = lo + 4;
                 if (lo >= shift && hi <= shift + win_len) {
-                    st_stream_u4(reinterpret_cast<uint4 *>(dst_al + lo), *reinterpret_cast<const uint4 *>(s.stage + lo));
+                    st_stream_u32(reinterpret_cast<uint32_t *>(dst_al + lo), v);
                 } else {
-                    for (uint32_t k = max(lo, shift); k < min(hi, shift + win_len); k++) dst_al[k] = s.stage[k];
+                    for (uint32_t k = max(lo, shift); k < min(hi, shift + win_len); k++)
+                        dst_al[k] = static_cast<uint8_t>(v >> (8 * (k - lo)));
                 }
             }
             __syncthreads();

@@ -72,16 +72,19 @@ struct hb_ctx {
     // histogram
     unsigned long long *d_hist = nullptr;
     int hist_grid = 0;
-    int hist_variant = 0;
+    int hist_ctas_per_sm = 1;
+    // per-region histograms of the last hb_histogram call (consumed by the encoder)
+    uint32_t *d_region_hist = nullptr;   // [sm_count][256]
+    const uint8_t *region_ptr = nullptr;
+    size_t region_n = 0, region_letters = 0;
+    bool region_valid = false;
 
     // encoder
     hb::EncTable *d_enc_table = nullptr;
     hb_tree enc_tree_cached;
     bool enc_tree_valid = false;
     int enc_chunk = 4;                   // letters per chunk: 4 (codes <= 16 bits), 2 (<= 32), 1 (<= 64)
-    DevBuf<uint64_t> enc_desc;           // one look-back descriptor per tile
     unsigned long long *d_total_bits = nullptr;
-    int enc_grid = 0;                    // co-resident CTAs (cooperative launch)
 
     // decoder
     hb::DecTables *d_dec_tables = nullptr;
@@ -122,19 +125,41 @@ bool same_nodes(const hb_tree &a, const hb_tree &b) {
 }
 
 // ---------------------------------------------------------------- histogram
+size_t region_size_for(const hb_ctx *ctx, size_t n) {
+    const size_t unit = hb::kEncRoundLetters;
+    const size_t per = (n + ctx->sm_count - 1) / ctx->sm_count;
+    return std::max<size_t>(unit, (per + unit - 1) / unit * unit);
+}
+
 hb_status launch_hist(hb_ctx *ctx, const uint8_t *d_data, size_t n, unsigned long long *d_hist) {
     HB_CUDA(cudaMemsetAsync(d_hist, 0, 256 * sizeof(unsigned long long), ctx->stream));
-    // per-CTA partials are u32: keep every launch below 2^32 bytes per CTA
+    ctx->region_valid = false;
+    if (n == 0) return HB_OK;
+    const size_t region = region_size_for(ctx, n);
+    if ((reinterpret_cast<uintptr_t>(d_data) & 15) == 0 && region < (static_cast<size_t>(1) << 32)) {
+        // region variant: global bins + one 256 x u32 histogram per encoder region
+        const int n_regions = static_cast<int>((n + region - 1) / region);
+        HB_CUDA(cudaMemsetAsync(ctx->d_region_hist, 0, static_cast<size_t>(ctx->sm_count) * 256 * sizeof(uint32_t), ctx->stream));
+        const size_t vecs_per_region = region / 16;
+        int per = static_cast<int>(std::min<size_t>(ctx->hist_ctas_per_sm, (vecs_per_region + hb::kHistThreads - 1) / hb::kHistThreads));
+        if (per < 1) per = 1;
+        hb::hist_regions_kernel<<<n_regions * per, hb::kHistThreads, 0, ctx->stream>>>(d_data, n, region, per, d_hist, ctx->d_region_hist);
+        ctx->launches++;
+        HB_CUDA(cudaGetLastError());
+        ctx->region_ptr = d_data;
+        ctx->region_n = n;
+        ctx->region_letters = region;
+        ctx->region_valid = true;
+        return HB_OK;
+    }
+    // any alignment: per-CTA partials are u32, keep every launch below 2^32 bytes per CTA
     const size_t max_piece = static_cast<size_t>(1) << 36;
     for (size_t off = 0; off < n; off += max_piece) {
         const size_t len = std::min(max_piece, n - off);
         const size_t vecs = len / 16 + 1;
         int grid = static_cast<int>(std::min<size_t>(ctx->hist_grid, (vecs + hb::kHistThreads - 1) / hb::kHistThreads));
         if (grid < 1) grid = 1;
-        if (ctx->hist_variant == 1)
-            hb::hist_warp_private_kernel<<<grid, hb::kHistThreads, 0, ctx->stream>>>(d_data + off, len, d_hist);
-        else
-            hb::hist_lane_columns_kernel<<<grid, hb::kHistThreads, 0, ctx->stream>>>(d_data + off, len, d_hist);
+        hb::hist_lane_columns_kernel<<<grid, hb::kHistThreads, 0, ctx->stream>>>(d_data + off, len, d_hist);
         ctx->launches++;
         HB_CUDA(cudaGetLastError());
     }
@@ -166,22 +191,17 @@ hb_status upload_enc_table(hb_ctx *ctx, const hb_tree *tree) {
 template <int S>
 hb_status launch_encode_s(hb_ctx *ctx, const uint8_t *d_data, size_t n, uint32_t start_bit, uint8_t *d_out,
                           unsigned long long *d_total_bits) {
-    const size_t tile = static_cast<size_t>(32) * hb::kEncRounds * S;
-    const size_t n_tiles = (n + tile - 1) / tile;
-    if (n_tiles > 0xFFFFFFF0ull) return HB_ERR_INVALID_ARG;
-    HB_TRY(ctx->enc_desc.reserve(n_tiles));
-    HB_CUDA(cudaMemsetAsync(ctx->enc_desc.p, 0, n_tiles * sizeof(uint64_t), ctx->stream));
-    const size_t ctas_needed = (n_tiles + hb::kEncWarps - 1) / hb::kEncWarps;
-    const int grid = static_cast<int>(std::min<size_t>(ctx->enc_grid, ctas_needed));
-    const hb::EncTable *table = ctx->d_enc_table;
-    uint32_t *out32 = reinterpret_cast<uint32_t *>(d_out);
-    uint64_t *desc = ctx->enc_desc.p;
-    uint32_t nt = static_cast<uint32_t>(n_tiles);
-    void *args[] = {&d_data, &n, &table, &start_bit, &out32, &desc, &nt, &d_total_bits};
-    // cooperative launch = all CTAs co-resident, which the tile look-back relies on
-    HB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(hb::encode_warp_tiles_kernel<S>), dim3(grid),
-                                        dim3(hb::kEncThreads), args, hb::enc_smem_bytes(S), ctx->stream));
+    // the encoder needs the per-region histograms of exactly this input
+    if (!(ctx->region_valid && ctx->region_ptr == d_data && ctx->region_n == n)) {
+        HB_TRY(launch_hist(ctx, d_data, n, ctx->d_hist));
+        if (!ctx->region_valid) return HB_ERR_INVALID_ARG;
+    }
+    const int n_regions = static_cast<int>((n + ctx->region_letters - 1) / ctx->region_letters);
+    hb::encode_regions_kernel<S><<<n_regions, hb::kEncThreads, hb::enc_smem_bytes(S), ctx->stream>>>(
+        d_data, n, ctx->d_enc_table, start_bit, reinterpret_cast<uint32_t *>(d_out), ctx->d_region_hist,
+        ctx->region_letters, d_total_bits);
     ctx->launches++;
+    HB_CUDA(cudaGetLastError());
     return HB_OK;
 }
 
@@ -425,11 +445,10 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
     if (!ctx) return HB_ERR_NO_MEM;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    const char *hv = std::getenv("HB_HIST_VARIANT");
-    ctx->hist_variant = hv ? std::atoi(hv) : 0;
     hb_status rc = [&]() -> hb_status {
         HB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         HB_CUDA(cudaMalloc(&ctx->d_hist, 256 * sizeof(unsigned long long)));
+        HB_CUDA(cudaMalloc(&ctx->d_region_hist, static_cast<size_t>(ctx->sm_count) * 256 * sizeof(uint32_t)));
         HB_CUDA(cudaMalloc(&ctx->d_enc_table, sizeof(hb::EncTable)));
         HB_CUDA(cudaMalloc(&ctx->d_total_bits, sizeof(unsigned long long)));
         HB_CUDA(cudaMalloc(&ctx->d_dec_tables, sizeof(hb::DecTables)));
@@ -442,20 +461,12 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
         HB_CUDA(cudaFuncSetAttribute(hb::dec_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::kDecSmemCount)));
         HB_CUDA(cudaFuncSetAttribute(hb::dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::kDecSmemWrite)));
         int occ = 0;
-        if (ctx->hist_variant == 1)
-            HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::hist_warp_private_kernel, hb::kHistThreads, 0));
-        else
-            HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::hist_lane_columns_kernel, hb::kHistThreads, 0));
-        ctx->hist_grid = ctx->sm_count * std::max(occ, 1);
-        HB_CUDA(cudaFuncSetAttribute(hb::encode_warp_tiles_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::enc_smem_bytes(4))));
-        HB_CUDA(cudaFuncSetAttribute(hb::encode_warp_tiles_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::enc_smem_bytes(2))));
-        HB_CUDA(cudaFuncSetAttribute(hb::encode_warp_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::enc_smem_bytes(1))));
-        HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::encode_warp_tiles_kernel<1>, hb::kEncThreads, hb::enc_smem_bytes(1)));
-        if (occ < 1) { g_last_error = "encode kernel does not fit on an SM"; return HB_ERR_CUDA; }
-        ctx->enc_grid = ctx->sm_count;                            // one persistent CTA per SM
-        int coop = 0;
-        HB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
-        if (!coop) { g_last_error = "device lacks cooperative launch"; return HB_ERR_CUDA; }
+        HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::hist_lane_columns_kernel, hb::kHistThreads, 0));
+        ctx->hist_ctas_per_sm = std::max(occ, 1);
+        ctx->hist_grid = ctx->sm_count * ctx->hist_ctas_per_sm;
+        HB_CUDA(cudaFuncSetAttribute(hb::encode_regions_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::enc_smem_bytes(4))));
+        HB_CUDA(cudaFuncSetAttribute(hb::encode_regions_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::enc_smem_bytes(2))));
+        HB_CUDA(cudaFuncSetAttribute(hb::encode_regions_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::enc_smem_bytes(1))));
         HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::dec_count_kernel, hb::kDecThreads, hb::kDecSmemCount));
         ctx->dec_count_grid = ctx->sm_count * std::max(occ, 1);
         HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::dec_write_kernel, hb::kDecThreads, hb::kDecSmemWrite));
@@ -471,12 +482,11 @@ hb_status hb_ctx_destroy(hb_ctx *ctx) {
     if (!ctx) return HB_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_hist); cudaFree(ctx->d_enc_table); cudaFree(ctx->d_total_bits); cudaFree(ctx->d_dec_tables);
+    cudaFree(ctx->d_hist); cudaFree(ctx->d_region_hist); cudaFree(ctx->d_enc_table); cudaFree(ctx->d_total_bits); cudaFree(ctx->d_dec_tables);
     cudaFree(ctx->d_dec_result); cudaFree(ctx->d_n_dirty);
     if (ctx->h_dec_result) cudaFreeHost(ctx->h_dec_result);
     if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
     if (ctx->h_total_bits) cudaFreeHost(ctx->h_total_bits);
-    ctx->enc_desc.release();
     ctx->sub_info.release(); ctx->blk_count.release(); ctx->blk_local.release(); ctx->dirty.release();
     ctx->blk_entry.release(); ctx->blk_exit.release(); ctx->group_total.release();
     ctx->stage_in.release(); ctx->stage_out.release();

@@ -1,25 +1,25 @@
 // hb_encode.cuh -- K2: the packing loop of compress_with_tree (comp.rs:422-447) as one single-pass kernel.
 //
-// The reference appends each letter's code bit by bit, MSB first, to one gap-free stream.  Here every WARP is
-// autonomous (no CTA barrier in the steady state):
-//   * one persistent CTA per SM; warp g of the grid owns tiles g, g + G, g + 2G, ... (G = warps in the grid, all
-//     co-resident: the kernel is launched cooperatively so the look-back below can never wait on a warp that is
-//     not running);
+// The reference appends each letter's code bit by bit, MSB first, to one gap-free stream.  Here:
+//   * the input is cut into one contiguous REGION per CTA (one persistent CTA per SM).  The histogram kernel
+//     (hb_hist.cuh) has already counted every region separately, so the exact bit offset of region r is
+//     sum_{i<r} sum_b region_hist[i][b] * len[b]: every CTA computes its own base in a short prologue.  There is no
+//     inter-CTA communication at all (no look-back descriptors, no cooperative launch, nothing to wait on);
+//   * inside a region the 32 warps of the CTA take 32 consecutive TILES per round; one __syncthreads per round
+//     exchanges the 32 tile bit totals through shared memory and every warp derives its 64-bit global bit offset;
 //   * a tile is 32 lanes x 8 rounds of CHUNKS; a chunk is S consecutive letters (S = 4 when every code has <= 16
-//     bits, 2 for <= 32 bits, 1 for <= 64 bits) merged into one <= 64-bit value.  In round r lane i takes chunk
-//     r*32 + i, so the 32 lanes of a round read 32*S consecutive bytes (coalesced) and write adjacent stream words;
+//     bits, 2 for <= 32 bits, 1 for <= 64 bits) merged into one <= 64-bit value.  Lane i takes chunk r*32 + i in
+//     round r, so the 32 lanes read 32*S consecutive bytes (coalesced) and write adjacent stream words;
 //   * codes come from a lane-replicated shared-memory table: entry (b, lane) lives at [b*32 + lane] as (code, len),
 //     so the 32 lookups of a warp never conflict whatever the data;
 //   * a warp scan of the chunk lengths (two rounds packed per 32-bit scan) gives every chunk its bit offset inside the
-//     tile; the tile total is published at once (status AGGREGATE) so successors never wait on the packing;
-//   * chunks are OR-ed into a per-warp shared-memory staging stream (<= 3 shared atomics per chunk);
-//   * a decoupled look-back over one 64-bit descriptor per tile yields the tile's 64-bit GLOBAL bit offset;
+//     tile; chunks are OR-ed into a per-warp shared-memory staging stream (<= 3 shared atomics per chunk);
 //   * the staging stream is tile-local; on the way out it is funnel-shifted by (global offset % 32) and stored as
 //     coalesced big-endian 32-bit words.  The word two tiles share is written once, by the later tile, which
 //     re-derives the last 32 bits of its predecessor from the predecessor's last 32 letters (every code has >= 1
-//     bit) instead of waiting for them: no pre-zeroed output, no global atomics, no second pass over the input.
+//     bit): no pre-zeroed output, no global atomics, no second pass over the input.
 //
-// Algorithmic HBM bytes per launch: N (letters read once) + C (stream written once).
+// Algorithmic HBM bytes per launch: N (letters read once) + C (stream written once) (+ 1 KiB per region of counts).
 #pragma once
 
 #include "hb_common.cuh"
@@ -31,9 +31,7 @@ constexpr int kEncThreads = kEncWarps * 32;
 constexpr int kEncRounds = 8;                                   // chunks per lane per tile
 constexpr int kEncStageWords = 32 * kEncRounds * 2 + 8;         // 256 chunks x 64 bits, + tail slot + slack
 
-constexpr uint64_t kDescAggregate = 1ull << 62;
-constexpr uint64_t kDescPrefix = 2ull << 62;
-constexpr uint64_t kDescValueMask = (1ull << 62) - 1;
+constexpr int kEncRoundLetters = kEncWarps * 32 * kEncRounds * 4;   // region sizes are multiples of this (S = 4 round)
 
 // device-resident code table
 struct EncTable {
@@ -45,6 +43,22 @@ constexpr size_t enc_smem_bytes(int S) {
     return 256 * 32 * sizeof(uint2) + (S == 1 ? 256 * sizeof(uint32_t) : 0) + kEncWarps * kEncStageWords * sizeof(uint32_t);
 }
 
+// exact bit count of a region from its histogram: sum_b hist[b] * len[b]  (block-wide, all threads get the result)
+__device__ __forceinline__ unsigned long long enc_region_base(const uint32_t *__restrict__ region_hist, uint32_t n_before,
+                                                              const uint2 *s_tab_lane0, unsigned long long *s_red) {
+    unsigned long long acc = 0;
+    for (uint32_t k = threadIdx.x; k < n_before * 256u; k += blockDim.x)
+        acc += static_cast<unsigned long long>(region_hist[k]) * s_tab_lane0[(k & 255u) << 5].y;
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, sft);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    unsigned long long total = 0;
+    for (uint32_t k = 0; k < blockDim.x / 32; k++) total += s_red[k];
+    __syncthreads();
+    return total;
+}
+
 template <int S> struct EncLoad;
 template <> struct EncLoad<4> { using type = uint32_t; };
 template <> struct EncLoad<2> { using type = uint16_t; };
@@ -54,27 +68,36 @@ extern __shared__ __align__(16) uint8_t enc_smem[];
 
 template <int S>
 __global__ void __launch_bounds__(kEncThreads, 1)
-encode_warp_tiles_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable *__restrict__ table,
-                         uint32_t start_bit, uint32_t *__restrict__ out32, uint64_t *__restrict__ desc,
-                         uint32_t n_tiles, unsigned long long *__restrict__ total_bits_out) {
+encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable *__restrict__ table,
+                      uint32_t start_bit, uint32_t *__restrict__ out32, const uint32_t *__restrict__ region_hist,
+                      size_t region_letters, unsigned long long *__restrict__ total_bits_out) {
     constexpr int kTile = 32 * kEncRounds * S;                  // letters per tile: 1024 / 512 / 256
     using load_t = typename EncLoad<S>::type;
 
     uint2 *s_tab = reinterpret_cast<uint2 *>(enc_smem);                                     // [256][32]
     uint32_t *s_hi = reinterpret_cast<uint32_t *>(enc_smem + 256 * 32 * sizeof(uint2));    // [256] (S == 1)
     uint32_t *s_stage_all = s_hi + (S == 1 ? 256 : 0);
+    __shared__ unsigned long long s_red[kEncWarps];
+    __shared__ uint32_t s_tile_bits[2][kEncWarps];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 256 * 32; i += kEncThreads) s_tab[i] = table->lo[i >> 5];
     if (S == 1) for (int i = threadIdx.x; i < 256; i += kEncThreads) s_hi[i] = table->hi[i];
-    __syncthreads();                                            // the only CTA barrier
+    __syncthreads();
+
+    const size_t region_begin = static_cast<size_t>(blockIdx.x) * region_letters;
+    if (region_begin >= n) return;
+    const size_t region_end = min(n, region_begin + region_letters);
+    // global bit offset of this region: everything the regions before it emit (+ the caller's start bit)
+    unsigned long long running = start_bit + enc_region_base(region_hist, blockIdx.x, s_tab, s_red);
 
     uint32_t *stage = s_stage_all + warp * kEncStageWords;      // [0] = predecessor tail, [1 + m] = local word m
     const uint2 *my_tab = s_tab + lane;
-    const uint32_t grid_warps = gridDim.x * kEncWarps;
+    const uint32_t n_rounds = static_cast<uint32_t>((region_end - region_begin + kEncWarps * kTile - 1) / (kEncWarps * kTile));
 
-    for (uint32_t tile = blockIdx.x * kEncWarps + warp; tile < n_tiles; tile += grid_warps) {
-        const size_t tile_base = static_cast<size_t>(tile) * kTile;
+    for (uint32_t round = 0; round < n_rounds; round++) {
+        const size_t tile_base = region_begin + (static_cast<size_t>(round) * kEncWarps + warp) * kTile;
+        const bool live = tile_base < region_end;               // region_end == n whenever a tile is cut short
         const bool full = tile_base + kTile <= n;
 
         // ---- load this lane's 8 chunks (round r: chunk r*32 + lane) and merge each chunk's codes
@@ -149,11 +172,20 @@ encode_warp_tiles_kernel(const uint8_t *__restrict__ data, size_t n, const EncTa
             tile_bits += tot >> 16;
         }
 
-        // ---- publish the aggregate right away; successors only need this to get past us
-        if (lane == 0) {
-            if (tile == 0) st_release_u64(desc, kDescPrefix | (static_cast<unsigned long long>(start_bit) + tile_bits));
-            else st_release_u64(desc + tile, kDescAggregate | tile_bits);
+        // ---- one barrier per round: exchange the 32 tile totals, derive this tile's global bit offset
+        if (!live) tile_bits = 0;
+        if (lane == 0) s_tile_bits[round & 1][warp] = tile_bits;
+        __syncthreads();
+        unsigned long long excl;
+        {
+            const uint32_t mine = s_tile_bits[round & 1][lane];
+            const uint32_t incl = warp_incl_scan(mine);
+            const uint32_t before = __shfl_sync(0xFFFFFFFFu, incl - mine, warp);
+            const uint32_t round_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            excl = running + before;
+            running += round_total;
         }
+        if (!live) continue;
 
         // ---- OR the chunks into the zeroed staging stream
         const uint32_t n_local_words = (tile_bits + 31) / 32 + 3;
@@ -174,7 +206,7 @@ encode_warp_tiles_kernel(const uint8_t *__restrict__ data, size_t n, const EncTa
 
         // ---- last 32 bits of the predecessor tile, recomputed from its last 32 letters
         uint32_t pred_tail = 0;
-        if (tile > 0) {
+        if (tile_base > 0) {
             const uint32_t b = data[tile_base - 32 + lane];
             const uint2 e = my_tab[b << 5];
             // suffix sum of the lengths of the letters after mine
@@ -189,35 +221,10 @@ encode_warp_tiles_kernel(const uint8_t *__restrict__ data, size_t n, const EncTa
             pred_tail = __reduce_or_sync(0xFFFFFFFFu, piece);
         }
 
-        // ---- decoupled look-back: exclusive global bit offset of this tile
-        unsigned long long excl = start_bit;
-        if (tile > 0) {
-            excl = 0;
-            long long look = static_cast<long long>(tile) - 1;
-            for (;;) {
-                const long long idx = look - lane;
-                unsigned long long d = kDescPrefix;            // virtual "prefix 0" before tile 0 (never the nearest)
-                if (idx >= 0) {
-                    uint32_t polls = 0;
-                    do {
-                        d = ld_acquire_u64(desc + idx);
-                        if (++polls == (1u << 26)) asm volatile("trap;");   // a lost descriptor must not hang the GPU
-                    } while ((d >> 62) == 0);
-                }
-                const unsigned pm = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2);
-                const int first_prefix = pm ? __ffs(pm) - 1 : 32;
-                unsigned long long contrib = (lane <= first_prefix) ? (d & kDescValueMask) : 0ull;
-#pragma unroll
-                for (int sft = 16; sft > 0; sft >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, sft);
-                excl += contrib;
-                if (pm) break;
-                look -= 32;
-            }
-            if (lane == 0) st_release_u64(desc + tile, kDescPrefix | (excl + tile_bits));
-        }
+        const bool is_last_tile = tile_base + kTile >= n;
         if (lane == 0) {
             stage[0] = pred_tail;
-            if (tile == n_tiles - 1 && total_bits_out) *total_bits_out = excl + tile_bits - start_bit;
+            if (is_last_tile && total_bits_out) *total_bits_out = excl + tile_bits - start_bit;
         }
         __syncwarp();
 
@@ -229,7 +236,7 @@ encode_warp_tiles_kernel(const uint8_t *__restrict__ data, size_t n, const EncTa
         uint32_t *dst = out32 + w0;
         for (uint32_t m = lane; m < n_full; m += 32)
             st_stream_u32(dst + m, bswap32(__funnelshift_r(stage[1 + m], stage[m], rr)));
-        if (tile == n_tiles - 1 && (end_bit & 31) && lane == 0) {
+        if (is_last_tile && (end_bit & 31) && lane == 0) {
             // the stream's final partial word: pad bits are zero (comp.rs:446-447), write only the bytes that exist
             const uint32_t word = __funnelshift_r(stage[1 + n_full], stage[n_full], rr);
             const uint32_t n_bytes = (static_cast<uint32_t>(end_bit & 31) + 7) / 8;

@@ -84,44 +84,60 @@ hist_lane_columns_kernel(const uint8_t *__restrict__ data, size_t n, unsigned lo
     }
 }
 
-// Comparison variant kept for profiling only (profiles/): classic per-warp private 256-bin histograms with data-
-// dependent bank and address conflicts.  Selected with HB_HIST_VARIANT=1.
+// Region variant used by compress(): the input is cut into `n_regions` contiguous regions (one per encoder CTA) and,
+// besides the global 256-bin result, every region gets its own 256 x u32 histogram.  The encoder turns those into the
+// exact bit offset of every region (sum_b region_hist[r][b] * len[b]) without reading the input a second time and
+// without any inter-CTA look-back.  `data` must be 16-byte aligned; region_bytes is a multiple of 16.
+// grid = n_regions * ctas_per_region.
 __global__ void __launch_bounds__(kHistThreads)
-hist_warp_private_kernel(const uint8_t *__restrict__ data, size_t n, unsigned long long *__restrict__ hist) {
-    constexpr int kWarps = kHistThreads / 32;
-    __shared__ uint32_t bins[kWarps * 256];
-    for (int i = threadIdx.x; i < kWarps * 256; i += kHistThreads) bins[i] = 0;
+hist_regions_kernel(const uint8_t *__restrict__ data, size_t n, size_t region_bytes, int ctas_per_region,
+                    unsigned long long *__restrict__ hist, uint32_t *__restrict__ region_hist) {
+    __shared__ uint32_t cols[256 * 32];
+    for (int i = threadIdx.x; i < 256 * 32; i += kHistThreads) cols[i] = 0;
     __syncthreads();
-    uint32_t *mine = bins + (threadIdx.x >> 5) * 256;
+    const uint32_t lane_base = static_cast<uint32_t>(__cvta_generic_to_shared(cols)) + (lane_id() << 2);
 
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(data);
-    size_t head = (16 - (addr & 15)) & 15;
-    if (head > n) head = n;
-    const size_t n_vec = (n - head) / 16;
-    const size_t tail_begin = head + n_vec * 16;
-    const uint4 *vec = reinterpret_cast<const uint4 *>(data + head);
-    const size_t stride = static_cast<size_t>(gridDim.x) * kHistThreads;
-    for (size_t i = static_cast<size_t>(blockIdx.x) * kHistThreads + threadIdx.x; i < n_vec; i += stride) {
-        uint4 v = ld_stream_u4(vec + i);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t region = blockIdx.x / ctas_per_region, part = blockIdx.x % ctas_per_region;
+    const size_t begin = static_cast<size_t>(region) * region_bytes;
+    if (begin < n) {
+        const size_t end = min(n, begin + region_bytes);
+        const size_t n_vec = (end - begin) / 16;
+        const uint4 *vec = reinterpret_cast<const uint4 *>(data + begin);
+        const size_t stride = static_cast<size_t>(ctas_per_region) * kHistThreads;
+        size_t i = static_cast<size_t>(part) * kHistThreads + threadIdx.x;
+        for (; i + (kHistUnroll - 1) * stride < n_vec; i += kHistUnroll * stride) {
+            uint4 v[kHistUnroll];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            atomicAdd(mine + (w[k] & 0xFF), 1u);
-            atomicAdd(mine + ((w[k] >> 8) & 0xFF), 1u);
-            atomicAdd(mine + ((w[k] >> 16) & 0xFF), 1u);
-            atomicAdd(mine + (w[k] >> 24), 1u);
+            for (int u = 0; u < kHistUnroll; u++) v[u] = ld_stream_u4(vec + i + u * stride);
+#pragma unroll
+            for (int u = 0; u < kHistUnroll; u++) {
+                hist_word(lane_base, v[u].x);
+                hist_word(lane_base, v[u].y);
+                hist_word(lane_base, v[u].z);
+                hist_word(lane_base, v[u].w);
+            }
         }
-    }
-    if (blockIdx.x == 0) {
-        if (threadIdx.x < head) atomicAdd(mine + data[threadIdx.x], 1u);
-        const size_t n_tail = n - tail_begin;
-        if (threadIdx.x < n_tail) atomicAdd(mine + data[tail_begin + threadIdx.x], 1u);
+        for (; i < n_vec; i += stride) {
+            uint4 v = ld_stream_u4(vec + i);
+            hist_word(lane_base, v.x);
+            hist_word(lane_base, v.y);
+            hist_word(lane_base, v.z);
+            hist_word(lane_base, v.w);
+        }
+        const size_t tail_begin = begin + n_vec * 16;          // < 16 bytes, only in the last region
+        if (part == 0 && tail_begin + threadIdx.x < end)
+            hist_red(lane_base + (static_cast<uint32_t>(data[tail_begin + threadIdx.x]) << 7));
     }
     __syncthreads();
     if (threadIdx.x < 256) {
+        const uint32_t b = threadIdx.x;
         uint32_t sum = 0;
-        for (int wp = 0; wp < kWarps; wp++) sum += bins[wp * 256 + threadIdx.x];
-        if (sum) atomicAdd(hist + threadIdx.x, static_cast<unsigned long long>(sum));
+#pragma unroll
+        for (int j = 0; j < 32; j++) sum += cols[b * 32 + ((j + b) & 31)];
+        if (sum) {
+            atomicAdd(hist + b, static_cast<unsigned long long>(sum));
+            atomicAdd(region_hist + region * 256 + b, sum);
+        }
     }
 }
 

@@ -236,14 +236,13 @@ void build_dec_tables(const hb_tree *tree, hb::DecTables *t) {
                               : (static_cast<uint32_t>(nd.left) | (static_cast<uint32_t>(nd.right) << 16));
     }
     const uint32_t root = tree->root;
-    t->root_is_leaf = leaf(root);
+    t->root = root;
     const int K = hb::kLutBits;
     for (uint32_t p = 0; p < (1u << K); p++) {
         if (leaf(root)) {
             // comp.rs:496,506-509: a lone root emits its letter for every bit
             t->lut[p] = static_cast<uint16_t>(tree->nodes[root].letter | (1u << 8));
             t->cnt[p] = static_cast<uint8_t>((K << 4) | K);
-            t->lut2[p] = tree->nodes[root].letter | (static_cast<uint32_t>(tree->nodes[root].letter) << 8) | (1u << 16) | (2u << 24);
             continue;
         }
         // first code word
@@ -272,19 +271,6 @@ void build_dec_tables(const hb_tree *tree, hb::DecTables *t) {
             if (pos >= K) break;
         }
         t->cnt[p] = static_cast<uint8_t>((pos << 4) | letters);
-        // write-pass entry: up to two letters
-        if (!leaf(node)) { t->lut2[p] = 0; continue; }
-        const uint32_t len0 = static_cast<uint32_t>(used);
-        uint32_t e = tree->nodes[node].letter | (len0 << 16);
-        uint32_t nd2 = root;
-        int q2 = used;
-        while (q2 < K && !leaf(nd2)) {
-            const int bit = (p >> (K - 1 - q2)) & 1;
-            nd2 = bit ? tree->nodes[nd2].right : tree->nodes[nd2].left;
-            q2++;
-        }
-        if (leaf(nd2) && q2 > used) e |= (static_cast<uint32_t>(tree->nodes[nd2].letter) << 8) | (static_cast<uint32_t>(q2) << 24);
-        t->lut2[p] = e;
     }
 }
 
@@ -345,6 +331,7 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
     p.stream_bit0 = stream_bit0;
     p.len_gcd = tree->len_gcd ? tree->len_gcd : 1;
     p.fixed_len = (tree->min_len == tree->max_len) ? tree->max_len : 0;
+    p.max_len = tree->max_len ? tree->max_len : 1;
     if (tree->nodes[tree->root].left == HB_NO_CHILD) { p.fixed_len = 1; p.len_gcd = 1; }
     p.first_block = static_cast<uint32_t>(first_block);
     p.n_blocks = static_cast<uint32_t>(n_blocks);
@@ -393,7 +380,7 @@ hb_status run_write_pass(hb_ctx *ctx, uint8_t *d_out, size_t out_cap) {
     const hb::DecParams &p = ctx->last_dec;
     const int grid = static_cast<int>(std::min<uint32_t>(ctx->dec_write_grid, p.n_blocks));
     hb::dec_write_kernel<<<grid, hb::kDecThreads, hb::kDecSmemWrite, ctx->stream>>>(
-        p, ctx->d_dec_tables, ctx->blk_local.p, ctx->group_total.p, d_out);
+        p, ctx->d_dec_tables, ctx->blk_local.p, ctx->group_total.p, d_out, ctx->last_dec_total);
     ctx->launches++;
     HB_CUDA(cudaGetLastError());
     return HB_OK;

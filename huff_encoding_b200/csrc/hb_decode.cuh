@@ -17,13 +17,17 @@
 //                with the corrected entry by dec_fix_kernel (rare: needs a code that fails to resynchronise
 //                within a whole 1024-bit halo; worst case = strictly sequential propagation, still exact).
 //   offsets      two small scan kernels turn per-CTA letter counts into 64-bit output offsets.
-//   write pass   (dec_write_kernel)  every thread decodes exactly its count letters from its true entry into a
-//                shared-memory window; windows are copied out with coalesced 128-bit stores (gap-free rewrite).
+//   write pass   (dec_write_kernel)  no shared-memory staging of the output: thread t owns the output bytes between
+//                the 32-byte boundaries at or after its first letter and at or after its successor's first letter.  It
+//                decodes from its true entry (discarding the < 32 letters before its first boundary, which its
+//                predecessor writes), packs 32 letters into eight registers with static byte inserts and stores one
+//                full 32-byte sector per lane with a 256-bit store (gap-free rewrite, every sector written once).
 //
 // Decoding uses a 12-bit first-level table (letter, length) with a tree walk behind it for longer codes (any depth),
 // and for the count pass a 12-bit multi-letter table (bits consumed, letters completed) that skips several
 // short codes per lookup.  Lookups and stream words come from shared memory (stream rows padded by one word per
-// 32 so that threads walking their own subsequence in lock step hit 32 different banks).
+// 32 so that threads walking their own subsequence in lock step hit 32 different banks).  The inner loops keep a
+// 64-bit bit window in registers and address shared memory through 32-bit shared-space pointers.
 //
 // Algorithmic HBM bytes: C + N.  This implementation moves 2C + N (the stream is read by both passes) plus 4 bytes
 // of per-subsequence metadata per 128 stream bytes.
@@ -39,22 +43,20 @@ constexpr int kSubBits = kSubWords * 32;
 constexpr int kChunkWords = kDecThreads * kSubWords;           // 8192 words = 32 KB per CTA
 constexpr int kHaloWords = 32;                                 // before and after the chunk
 constexpr int kWinWords = kHaloWords + kChunkWords + kHaloWords;
-constexpr int kWinPhys = kWinWords + (kWinWords >> 5) + 1;     // padded: phys(i) = i + i/32
+constexpr int kWinPhys = kWinWords + (kWinWords >> 5) + 4;     // padded: phys(i) = i + i/32 (+ slack for look-ahead)
 constexpr uint32_t kWinBits = kWinWords * 32u;
 constexpr int kLutBits = 12;
 constexpr uint32_t kEnd32 = 0xFFFFFFFFu;
 constexpr uint64_t kEnd64 = ~0ull;
 constexpr int kLookbackBits = 512;                             // in-CTA look-back window W (thread 0 uses the full halo)
-constexpr int kOutWindow = 49152;                              // letters staged per copy-out round in the write pass
 constexpr int kScanGroup = 1024;                               // CTAs per offset-scan group
+constexpr int kGroup = 32;                                     // letters per 256-bit store in the write pass
 
 struct DecTables {                     // device resident, built on the host from the hb_tree
     uint16_t lut[1 << kLutBits];       // bit15 = 0: letter | len << 8 ; bit15 = 1: node index to continue from
     uint8_t  cnt[1 << kLutBits];       // (bits consumed << 4) | letters completed, 0 if the first code is longer than 12
     uint32_t nodes[HB_MAX_NODES];      // left | right << 16 ; leaf: left = 0xFFFF, right = letter
-    uint32_t root_is_leaf;
-    uint32_t lut2[1 << kLutBits];      // write pass: letter0 | letter1 << 8 | len0 << 16 | len(0+1) << 24 (0 = no 2nd);
-                                       // len0 == 0: first code longer than 12 bits (slow path)
+    uint32_t root;
 };
 
 struct DecParams {
@@ -65,27 +67,75 @@ struct DecParams {
     int64_t  entry_bit;                // >= 0: known first code-word start (>= own_begin); < 0: speculate
     uint64_t stream_bit0;              // stream bit index of buffer bit 0 (phase of the gcd alignment)
     uint32_t len_gcd, fixed_len;       // gcd of code lengths; fixed_len != 0 when all codes have that length
+    uint32_t max_len;                  // longest code (bounds how far a thread may read past its subsequence)
     uint32_t first_block, n_blocks;    // CTAs cover chunks first_block .. first_block + n_blocks - 1
     uint32_t *sub_info;                // per subsequence (relative to first_block): entry_rel << 16 | count
     uint64_t *blk_entry, *blk_exit;    // per CTA, absolute buffer bits (kEnd64 = none)
     uint32_t *blk_count;               // per CTA letters
 };
 
-__device__ __forceinline__ uint32_t win_phys(uint32_t i) { return i + (i >> 5); }
+// ---------------------------------------------------------------- shared-space access (32-bit addresses in registers)
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+    uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+    uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v;
+}
+__device__ __forceinline__ void stg256(void *p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 
-__device__ __forceinline__ uint32_t win_peek32(const uint32_t *win, uint32_t q) {
+struct DecShared {                     // shared-space byte addresses
+    uint32_t win, lut, cnt, nodes;
+};
+
+__device__ __forceinline__ uint32_t win_word_addr(uint32_t win, uint32_t i) { return win + ((i + (i >> 5)) << 2); }
+__device__ __forceinline__ uint32_t win_bit(uint32_t win, uint32_t q) {
+    return (lds32(win_word_addr(win, q >> 5)) >> (31 - (q & 31))) & 1u;
+}
+
+// ---------------------------------------------------------------- register bit window
+struct BitReader {
+    uint32_t hi, lo;        // next `have` bits of the stream, MSB first, in hi:lo
+    uint32_t have, wi, q;   // valid bits, next word to load, stream position of the MSB of hi
+    __device__ __forceinline__ void init(uint32_t win, uint32_t q0) {
+        q = q0; wi = q0 >> 5;
+        const uint32_t s = q0 & 31;
+        const uint32_t w0 = lds32(win_word_addr(win, wi)), w1 = lds32(win_word_addr(win, wi + 1));
+        hi = __funnelshift_l(w1, w0, s);
+        lo = w1 << s;
+        have = 64 - s;
+        wi += 2;
+    }
+    __device__ __forceinline__ void refill(uint32_t win) {          // afterwards have >= 33
+        if (have <= 32) {                                            // all valid bits are in hi, lo == 0
+            const uint32_t w = lds32(win_word_addr(win, wi));
+            hi |= __funnelshift_rc(w, 0u, have);
+            lo = __funnelshift_rc(0u, w, have);
+            have += 32;
+            wi++;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek() const { return hi >> (32 - kLutBits); }
+    __device__ __forceinline__ void skip(uint32_t l) {               // l < 32
+        hi = __funnelshift_l(lo, hi, l);
+        lo <<= l;
+        have -= l;
+        q += l;
+    }
+};
+
+// Decode one code word starting at window bit q (table + tree walk, any length).  Returns its length, 0 if it would
+// end after q_avail.
+__device__ __noinline__ uint32_t dec_one_slow(DecShared s, uint32_t q, uint32_t q_avail, uint32_t &letter) {
     const uint32_t i = q >> 5;
-    return __funnelshift_l(win[win_phys(i + 1)], win[win_phys(i)], q & 31);
-}
-__device__ __forceinline__ uint32_t win_bit(const uint32_t *win, uint32_t q) {
-    return (win[win_phys(q >> 5)] >> (31 - (q & 31))) & 1u;
-}
-
-// Decode one code word starting at window bit q.  Returns its length (0 if it would end after q_avail).
-__device__ __forceinline__ uint32_t dec_one(const uint32_t *win, const uint16_t *lut, const uint32_t *nodes,
-                                            uint32_t q, uint32_t q_avail, uint32_t &letter) {
-    const uint32_t x = win_peek32(win, q);
-    const uint32_t e = lut[x >> (32 - kLutBits)];
+    const uint32_t x = __funnelshift_l(lds32(win_word_addr(s.win, i + 1)), lds32(win_word_addr(s.win, i)), q & 31);
+    const uint32_t e = lds16(s.lut + ((x >> (32 - kLutBits)) << 1));
     uint32_t len;
     if (!(e & 0x8000u)) {
         len = (e >> 8) & 0xFu;
@@ -94,70 +144,45 @@ __device__ __forceinline__ uint32_t dec_one(const uint32_t *win, const uint16_t 
         uint32_t node = e & 0x3FFu;
         len = kLutBits;
         for (;;) {
-            const uint32_t nd = nodes[node];
+            const uint32_t nd = lds32(s.nodes + (node << 2));
             if ((nd & 0xFFFFu) == 0xFFFFu) { letter = nd >> 16; break; }
             if (q + len >= q_avail) return 0;
-            node = win_bit(win, q + len) ? (nd >> 16) : (nd & 0xFFFFu);
+            node = win_bit(s.win, q + len) ? (nd >> 16) : (nd & 0xFFFFu);
             len++;
         }
     }
     return (q + len <= q_avail) ? len : 0;
 }
 
-// Register bit window over the staged stream: buf holds the next `have` bits, MSB first.
-struct BitReader {
-    const uint32_t *win;
-    unsigned long long buf;
-    uint32_t have, wi, q;
-    __device__ __forceinline__ void init(const uint32_t *w, uint32_t q0) {
-        win = w; q = q0; wi = q0 >> 5;
-        const uint32_t s = q0 & 31;
-        const unsigned long long two = (static_cast<unsigned long long>(win[win_phys(wi)]) << 32) | win[win_phys(wi + 1)];
-        buf = two << s;
-        have = 64 - s;
-        wi += 2;
-    }
-    __device__ __forceinline__ void refill() {          // afterwards have >= 33
-        if (have <= 32) {
-            buf |= static_cast<unsigned long long>(win[win_phys(wi)]) << (32 - have);
-            have += 32;
-            wi++;
-        }
-    }
-    __device__ __forceinline__ uint32_t peek() const { return static_cast<uint32_t>(buf >> (64 - kLutBits)); }
-    __device__ __forceinline__ void skip(uint32_t l) { buf <<= l; have -= l; q += l; }
-};
-
 // Advance from q over whole code words while q < q_stop; count them.  Returns the first code-word start >= q_stop,
 // or kEnd32 when a code word does not fit below q_avail.
-__device__ __forceinline__ uint32_t dec_run(const uint32_t *win, const uint16_t *lut, const uint8_t *cnt_lut,
-                                            const uint32_t *nodes, uint32_t q, uint32_t q_stop, uint32_t q_avail,
-                                            uint32_t &count) {
+__device__ __forceinline__ uint32_t dec_run(DecShared s, uint32_t q, uint32_t q_stop, uint32_t q_avail, uint32_t &count) {
     uint32_t n = 0;
     if (q == kEnd32) { count = 0; return kEnd32; }
     const uint32_t fast_stop = min(q_stop, q_avail);
     if (q + kLutBits <= fast_stop) {
+        const uint32_t last = fast_stop - kLutBits;                  // multi-letter steps while q <= last
         BitReader rd;
-        rd.init(win, q);
-        while (rd.q + kLutBits <= fast_stop) {
-            rd.refill();
-            const uint32_t c = cnt_lut[rd.peek()];
+        rd.init(s.win, q);
+        while (rd.q <= last) {
+            rd.refill(s.win);
+            const uint32_t c = lds8(s.cnt + rd.peek());
             if (c) {
                 rd.skip(c >> 4);
                 n += c & 15u;
-            } else {                                        // first code longer than 12 bits: tree walk, then re-prime
+            } else {                                                 // first code longer than 12 bits
                 uint32_t letter;
-                const uint32_t len = dec_one(win, lut, nodes, rd.q, q_avail, letter);
+                const uint32_t len = dec_one_slow(s, rd.q, q_avail, letter);
                 if (!len) { count = n; return kEnd32; }
                 n++;
-                rd.init(win, rd.q + len);
+                rd.init(s.win, rd.q + len);
             }
         }
         q = rd.q;
     }
     while (q < q_stop) {
         uint32_t letter;
-        const uint32_t len = dec_one(win, lut, nodes, q, q_avail, letter);
+        const uint32_t len = dec_one_slow(s, q, q_avail, letter);
         if (!len) { count = n; return kEnd32; }
         q += len;
         n++;
@@ -167,9 +192,7 @@ __device__ __forceinline__ uint32_t dec_run(const uint32_t *win, const uint16_t 
 }
 
 __device__ __forceinline__ void dec_load_tables(const DecTables *__restrict__ t, uint16_t *s_lut, uint8_t *s_cnt,
-                                                uint32_t *s_nodes, uint32_t *s_lut2 = nullptr) {
-    if (s_lut2)
-        for (int i = threadIdx.x; i < (1 << kLutBits); i += blockDim.x) s_lut2[i] = t->lut2[i];
+                                                uint32_t *s_nodes) {
     const uint32_t *src_lut = reinterpret_cast<const uint32_t *>(t->lut);
     uint32_t *dst_lut = reinterpret_cast<uint32_t *>(s_lut);
     for (int i = threadIdx.x; i < (1 << kLutBits) / 2; i += blockDim.x) dst_lut[i] = src_lut[i];
@@ -188,15 +211,14 @@ __device__ __forceinline__ void dec_load_window(const DecParams &p, uint32_t chu
         const long long gw = w_begin + i;
         uint32_t v = 0;
         if (gw >= 0 && static_cast<uint64_t>(gw) < p.n_words_readable) v = bswap32(ld_stream_u32(p.words + gw));
-        win[win_phys(i)] = v;
+        win[i + (i >> 5)] = v;
     }
-    if (threadIdx.x == 0) win[win_phys(kWinWords)] = 0;      // win_peek32 may touch one word past the window
+    if (threadIdx.x < 3) win[kWinWords + (kWinWords >> 5) + threadIdx.x] = 0;   // look-ahead slack past the window
 }
 
-// The count pass for one chunk.  entry_override: kEnd64-1 => none (speculate / use p.entry_bit).
+// The count pass for one chunk.
 __device__ void dec_count_block(const DecParams &p, uint32_t blk, uint64_t entry_override, bool use_override,
-                                uint32_t *win, const uint16_t *s_lut, const uint8_t *s_cnt, const uint32_t *s_nodes,
-                                uint32_t *s_exit, uint32_t *s_red) {
+                                uint32_t *win, DecShared s, uint32_t *s_exit, uint32_t *s_red) {
     const int t = threadIdx.x;
     const uint32_t chunk = p.first_block + blk;
     dec_load_window(p, chunk, win);
@@ -217,7 +239,7 @@ __device__ void dec_count_block(const DecParams &p, uint32_t blk, uint64_t entry
     const uint32_t q_lo = max(q_sub, q_own_begin);
     const uint32_t q_hi = min(q_sub + kSubBits, q_own_end);
     const bool active = q_lo < q_sub + kSubBits && (q_sub < q_own_end);   // subsequence intersects the owned range
-    const bool is_first = active && (q_own_begin >= q_sub) ;              // contains own_begin: no predecessor
+    const bool is_first = active && (q_own_begin >= q_sub);               // contains own_begin: no predecessor
     const bool has_pred = active && !is_first && t > 0;
 
     // ---- phase A: entry candidate
@@ -238,7 +260,7 @@ __device__ void dec_count_block(const DecParams &p, uint32_t blk, uint64_t entry
                 if (rem) q0 += p.len_gcd - rem;
             }
             uint32_t dummy;
-            entry = q0 >= q_lo ? q0 : dec_run(win, s_lut, s_cnt, s_nodes, q0, q_lo, q_avail, dummy);
+            entry = q0 >= q_lo ? q0 : dec_run(s, q0, q_lo, q_avail, dummy);
         }
     }
 
@@ -247,10 +269,7 @@ __device__ void dec_count_block(const DecParams &p, uint32_t blk, uint64_t entry
     bool redo = active;
     for (int round = 0;; round++) {
         if (round > kDecThreads + 1) asm volatile("trap;");   // cannot happen: thread t is final after t rounds
-        if (redo) {
-            exitq = dec_run(win, s_lut, s_cnt, s_nodes, entry, q_hi, q_avail, count);
-            if (entry != kEnd32 && entry >= q_hi) { exitq = entry; count = 0; }
-        }
+        if (redo) exitq = dec_run(s, entry, q_hi, q_avail, count);
         s_exit[t] = exitq;
         __syncthreads();
         redo = false;
@@ -267,10 +286,10 @@ __device__ void dec_count_block(const DecParams &p, uint32_t blk, uint64_t entry
     if (active && entry != kEnd32) entry_rel = entry - q_sub;              // < max code length + alignment slack
     p.sub_info[sub] = (entry_rel << 16) | (active ? count : 0u);
 
-    // CTA totals: letters, entry of the first active thread, exit of the last thread
+    // CTA totals: letters, entry of the first active thread, exit of the last active thread
     uint32_t c = active ? count : 0u;
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, s);
+    for (int sft = 16; sft > 0; sft >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, sft);
     if ((t & 31) == 0) s_red[t >> 5] = c;
     __syncthreads();
     if (t == 0) {
@@ -287,37 +306,40 @@ __device__ void dec_count_block(const DecParams &p, uint32_t blk, uint64_t entry
 
 extern __shared__ __align__(16) uint8_t dec_smem[];
 
-struct DecSmem {
-    uint32_t *win; uint16_t *lut; uint8_t *cnt; uint32_t *nodes; uint32_t *exit; uint32_t *red; uint32_t *lut2; uint32_t *stage;
-};
 constexpr size_t dec_align16(size_t x) { return (x + 15) & ~static_cast<size_t>(15); }
 constexpr size_t kDecOffLut = dec_align16(kWinPhys * 4);
 constexpr size_t kDecOffNodes = kDecOffLut + (1 << kLutBits) * 2;
 constexpr size_t kDecOffRed = kDecOffNodes + dec_align16(HB_MAX_NODES * 4);
-constexpr size_t kDecOffVar = kDecOffRed + 64;                       // count: cnt + exit ; write: lut2 + stage
-constexpr size_t kDecSmemCount = kDecOffVar + (1 << kLutBits) + kDecThreads * 4;
-constexpr int kStageWords = kOutWindow / 4 + 32;                     // + slack for the 4-byte alignment shift, XOR-swizzled rows
-constexpr size_t kDecSmemWrite = kDecOffVar + (1 << kLutBits) * 4 + kStageWords * 4;
+constexpr size_t kDecOffCnt = kDecOffRed + 64;
+constexpr size_t kDecOffExit = kDecOffCnt + (1 << kLutBits);
+constexpr size_t kDecSmemCount = kDecOffExit + kDecThreads * 4;
+constexpr size_t kDecSmemWrite = kDecOffCnt;                           // window + lut + nodes + red
 
-__device__ __forceinline__ DecSmem dec_carve(uint8_t *base) {
-    DecSmem s;
-    s.win = reinterpret_cast<uint32_t *>(base);
-    s.lut = reinterpret_cast<uint16_t *>(base + kDecOffLut);
-    s.nodes = reinterpret_cast<uint32_t *>(base + kDecOffNodes);
-    s.red = reinterpret_cast<uint32_t *>(base + kDecOffRed);
-    s.cnt = base + kDecOffVar;
-    s.exit = reinterpret_cast<uint32_t *>(base + kDecOffVar + (1 << kLutBits));
-    s.lut2 = reinterpret_cast<uint32_t *>(base + kDecOffVar);
-    s.stage = reinterpret_cast<uint32_t *>(base + kDecOffVar + (1 << kLutBits) * 4);
-    return s;
+struct DecCarve {
+    uint32_t *win; uint16_t *lut; uint8_t *cnt; uint32_t *nodes; uint32_t *exit; uint32_t *red;
+    DecShared sh;
+};
+__device__ __forceinline__ DecCarve dec_carve(uint8_t *base) {
+    DecCarve c;
+    c.win = reinterpret_cast<uint32_t *>(base);
+    c.lut = reinterpret_cast<uint16_t *>(base + kDecOffLut);
+    c.nodes = reinterpret_cast<uint32_t *>(base + kDecOffNodes);
+    c.red = reinterpret_cast<uint32_t *>(base + kDecOffRed);
+    c.cnt = base + kDecOffCnt;
+    c.exit = reinterpret_cast<uint32_t *>(base + kDecOffExit);
+    c.sh.win = smem_addr(c.win);
+    c.sh.lut = smem_addr(c.lut);
+    c.sh.cnt = smem_addr(c.cnt);
+    c.sh.nodes = smem_addr(c.nodes);
+    return c;
 }
 
 __global__ void __launch_bounds__(kDecThreads)
 dec_count_kernel(DecParams p, const DecTables *__restrict__ tables) {
-    DecSmem s = dec_carve(dec_smem);
-    dec_load_tables(tables, s.lut, s.cnt, s.nodes);
+    DecCarve c = dec_carve(dec_smem);
+    dec_load_tables(tables, c.lut, c.cnt, c.nodes);
     for (uint32_t blk = blockIdx.x; blk < p.n_blocks; blk += gridDim.x)
-        dec_count_block(p, blk, 0, false, s.win, s.lut, s.cnt, s.nodes, s.exit, s.red);
+        dec_count_block(p, blk, 0, false, c.win, c.sh, c.exit, c.red);
 }
 
 // dirty[j] = 1 when CTA j's entry is not its predecessor's exit.  n_dirty accumulates.
@@ -333,9 +355,9 @@ __global__ void dec_verify_kernel(DecParams p, uint32_t *dirty, uint32_t *n_dirt
 // Serial repair of mismatching CTAs (single CTA).  Each repaired chunk may change its exit and dirty its successor.
 __global__ void __launch_bounds__(kDecThreads)
 dec_fix_kernel(DecParams p, const DecTables *__restrict__ tables, uint32_t *dirty) {
-    DecSmem s = dec_carve(dec_smem);
+    DecCarve c = dec_carve(dec_smem);
     __shared__ uint32_t s_next;
-    dec_load_tables(tables, s.lut, s.cnt, s.nodes);
+    dec_load_tables(tables, c.lut, c.cnt, c.nodes);
     uint32_t cur = 1;
     for (;;) {
         // find the next dirty chunk at or after cur
@@ -351,13 +373,14 @@ dec_fix_kernel(DecParams p, const DecTables *__restrict__ tables, uint32_t *dirt
             __syncthreads();
             if (found != 0xFFFFFFFFu) break;
         }
+        __syncthreads();
         const uint32_t j = s_next;
         if (j == 0xFFFFFFFFu) break;
         const volatile uint64_t *vexit = p.blk_exit;
         const uint64_t old_exit = vexit[j];
         const uint64_t entry = vexit[j - 1];
         __syncthreads();
-        dec_count_block(p, j, entry, true, s.win, s.lut, s.cnt, s.nodes, s.exit, s.red);
+        dec_count_block(p, j, entry, true, c.win, c.sh, c.exit, c.red);
         if (threadIdx.x == 0) {
             dirty[j] = 0;
             if (j + 1 < p.n_blocks && vexit[j] != old_exit) dirty[j + 1] = 1;
@@ -413,91 +436,144 @@ dec_scan_totals_kernel(uint64_t *group_total, uint32_t n_groups, uint64_t *grand
     if (threadIdx.x == 0) *grand_total = s_carry;
 }
 
-// ---- write pass
-// staging bytes live in 32-bit words whose index is XOR-swizzled by its row, so that lanes writing at a stride of a
-// multiple of 128 bytes (uniform data: 128 letters per thread) still hit 32 different banks
-__device__ __forceinline__ uint32_t stage_word(uint32_t w) { return w ^ ((w >> 5) & 31u); }
-__device__ __forceinline__ void stage_put(uint32_t *stage, uint32_t a, uint32_t letter) {
-    reinterpret_cast<uint8_t *>(stage)[(stage_word(a >> 2) << 2) | (a & 3u)] = static_cast<uint8_t>(letter);
+// ---------------------------------------------------------------- write pass
+// Letter source that works anywhere: the staged window while the position is safely inside it, the stream in global
+// memory (bit-serial tree walk) once a thread has to read past its window (only with very long codes).
+// bit-serial walk from the root over global memory (comp.rs:496-509 literally); returns letter | bits consumed << 8
+__device__ __noinline__ uint32_t dec_one_global(const uint32_t *__restrict__ words, const uint32_t *__restrict__ nodes_g,
+                                                uint32_t root, unsigned long long pos) {
+    uint32_t nd = nodes_g[root];
+    if ((nd & 0xFFFFu) == 0xFFFFu) return (nd >> 16) | (1u << 8);            // lone root: one letter per bit
+    uint32_t used = 0;
+    while ((nd & 0xFFFFu) != 0xFFFFu) {
+        const unsigned long long b = pos + used;
+        const uint32_t bit = (bswap32(words[b >> 5]) >> (31 - (b & 31))) & 1u;
+        nd = nodes_g[bit ? (nd >> 16) : (nd & 0xFFFFu)];
+        used++;
+    }
+    return (nd >> 16) | (used << 8);
+}
+
+struct LetterSource {
+    DecShared s;
+    const uint32_t *words;
+    const uint32_t *nodes_g;
+    uint32_t root;
+    long long win_bit0;
+    BitReader rd;
+    uint32_t q_safe;        // window positions below this never read outside the staged words
+    bool global_mode;
+    unsigned long long gpos;
+};
+
+// one letter, any code length, any position (slow paths only: ragged ends, long codes, window overrun)
+__device__ __noinline__ uint32_t slow_next(LetterSource &src) {
+    if (src.global_mode || src.rd.q >= src.q_safe) {
+        if (!src.global_mode) { src.global_mode = true; src.gpos = static_cast<unsigned long long>(src.win_bit0 + src.rd.q); }
+        const uint32_t r = dec_one_global(src.words, src.nodes_g, src.root, src.gpos);
+        src.gpos += r >> 8;
+        return r & 0xFFu;
+    }
+    uint32_t letter = 0;
+    const uint32_t len = dec_one_slow(src.s, src.rd.q, kWinBits, letter);
+    src.rd.init(src.s.win, src.rd.q + len);
+    return letter;
 }
 
 __global__ void __launch_bounds__(kDecThreads)
 dec_write_kernel(DecParams p, const DecTables *__restrict__ tables, const uint32_t *__restrict__ blk_local,
-                 const uint64_t *__restrict__ group_off, uint8_t *__restrict__ out) {
-    DecSmem s = dec_carve(dec_smem);
+                 const uint64_t *__restrict__ group_off, uint8_t *__restrict__ out, uint64_t total_letters) {
+    DecCarve c = dec_carve(dec_smem);
     __shared__ uint32_t s_w[kDecThreads / 32];
-    dec_load_tables(tables, s.lut, nullptr, s.nodes, s.lut2);
+    dec_load_tables(tables, c.lut, nullptr, c.nodes);
     const int t = threadIdx.x;
+    const uintptr_t out_addr = reinterpret_cast<uintptr_t>(out);
+    // between two safety checks a thread reads at most one group of letters (+ refill look-ahead)
+    const uint32_t reach = (kGroup + 1) * min(p.max_len, 255u) + 96;
+    const uint32_t q_safe_group = kWinBits > reach ? kWinBits - reach : 0;
+
     for (uint32_t blk = blockIdx.x; blk < p.n_blocks; blk += gridDim.x) {
         __syncthreads();
         const uint32_t chunk = p.first_block + blk;
-        dec_load_window(p, chunk, s.win);
+        dec_load_window(p, chunk, c.win);
 
         const uint32_t info = p.sub_info[blk * kDecThreads + t];
         const uint32_t my_count = info & 0xFFFFu;
         const uint32_t entry_rel = info >> 16;
-        const long long win_bit0 = (static_cast<long long>(chunk) * kChunkWords - kHaloWords) * 32;
-        const long long q_av = static_cast<long long>(p.avail_bits) - win_bit0;
-        const uint32_t q_avail = q_av < 0 ? 0u : (q_av > static_cast<long long>(kWinBits) ? kWinBits : static_cast<uint32_t>(q_av));
 
         // CTA-wide exclusive scan of letter counts
         const uint32_t incl = warp_incl_scan(my_count);
         if ((t & 31) == 31) s_w[t >> 5] = incl;
         __syncthreads();                                     // also: window staged
-        uint32_t before = 0, total = 0;
-        for (int k = 0; k < kDecThreads / 32; k++) { if (k < (t >> 5)) before += s_w[k]; total += s_w[k]; }
-        const uint32_t my_off = before + incl - my_count;
-        const uint64_t out_base = group_off[blk / kScanGroup] + blk_local[blk];
+        uint32_t before = 0;
+        for (int k = 0; k < kDecThreads / 32; k++) if (k < (t >> 5)) before += s_w[k];
+        const uint64_t first = group_off[blk / kScanGroup] + blk_local[blk] + before + incl - my_count;   // my first letter
+        if (my_count == 0) continue;
 
-        BitReader rd;
-        if (my_count) rd.init(s.win, (kHaloWords + t * kSubWords) * 32u + entry_rel);
-        uint32_t produced = 0;
-        for (uint32_t win_start = 0; win_start < total; win_start += kOutWindow) {
-            const uint32_t win_len = min(static_cast<uint32_t>(kOutWindow), total - win_start);
-            uint8_t *dst = out + out_base + win_start;
-            const uint32_t shift = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst) & 3);   // word-align stage to dst
-            // my letters that fall into [win_start, win_start + win_len)
-            uint32_t limit = min(my_count, win_start + win_len > my_off ? win_start + win_len - my_off : 0u);
-            uint32_t a = shift + my_off + produced - win_start;                                  // staging byte address
-            while (produced < limit) {
-                rd.refill();
-                const uint32_t e = s.lut2[rd.peek()];
-                const uint32_t len0 = (e >> 16) & 0xFFu;
-                if (len0) {
-                    const uint32_t len01 = e >> 24;
-                    stage_put(s.stage, a, e & 0xFFu);
-                    if (len01 && produced + 1 < limit) {
-                        stage_put(s.stage, a + 1, (e >> 8) & 0xFFu);
-                        rd.skip(len01);
-                        produced += 2; a += 2;
-                    } else {
-                        rd.skip(len0);
-                        produced += 1; a += 1;
-                    }
-                } else {                                                                          // code longer than 12 bits
-                    uint32_t letter = 0;
-                    const uint32_t len = dec_one(s.win, s.lut, s.nodes, rd.q, q_avail, letter);
-                    stage_put(s.stage, a, letter);
-                    produced += 1; a += 1;
-                    rd.init(s.win, rd.q + len);
-                }
+        // output range I own: [lo, hi) = 32-byte boundaries at/after my first letter and at/after my successor's
+        const uint64_t next_first = first + my_count;
+        uint64_t lo = first + ((0 - (out_addr + first)) & 31);
+        uint64_t hi = next_first + ((0 - (out_addr + next_first)) & 31);
+        if (first == 0) lo = 0;                              // nobody precedes the first letter: its ragged head is mine
+        if (hi > total_letters) hi = total_letters;          // ragged tail of the whole output
+        if (lo >= hi) continue;
+
+        LetterSource src;
+        src.s = c.sh;
+        src.words = p.words;
+        src.nodes_g = tables->nodes;
+        src.root = tables->root;
+        src.win_bit0 = (static_cast<long long>(chunk) * kChunkWords - kHaloWords) * 32;
+        src.q_safe = kWinBits - (min(p.max_len, 255u) + 96);
+        src.global_mode = false;
+        src.gpos = 0;
+        src.rd.init(c.sh.win, (kHaloWords + t * kSubWords) * 32u + entry_rel);
+
+        uint64_t pos = first;
+        if (pos < lo && src.rd.q < q_safe_group) {                            // letters my predecessor writes (< 32)
+            BitReader rd = src.rd;
+            while (pos < lo) {
+                rd.refill(c.sh.win);
+                const uint32_t e = lds16(c.sh.lut + (rd.peek() << 1));
+                if (e & 0x8000u) break;
+                rd.skip((e >> 8) & 0xFu);
+                pos++;
             }
-            __syncthreads();
-            // copy out whole 32-bit words; the ragged first / last word byte by byte
-            const uint32_t n_words = (shift + win_len + 3) / 4;
-            uint8_t *dst_al = dst - shift;
-            for (uint32_t w = t; w < n_words; w += kDecThreads) {
-                const uint32_t v = s.stage[stage_word(w)];
-                const uint32_t lo = w * 4, hi = lo + 4;
-                if (lo >= shift && hi <= shift + win_len) {
-                    st_stream_u32(reinterpret_cast<uint32_t *>(dst_al + lo), v);
-                } else {
-                    for (uint32_t k = max(lo, shift); k < min(hi, shift + win_len); k++)
-                        dst_al[k] = static_cast<uint8_t>(v >> (8 * (k - lo)));
-                }
-            }
-            __syncthreads();
+            src.rd = rd;
         }
+        for (; pos < lo; pos++) (void)slow_next(src);
+        for (; pos < hi && ((out_addr + pos) & 31); pos++)                    // ragged head (first letter only)
+            out[pos] = static_cast<uint8_t>(slow_next(src));
+        while (pos + kGroup <= hi) {
+            bool done = false;
+            if (!src.global_mode && src.rd.q < q_safe_group) {
+                // fast path: 32 letters, branch-free body, static byte inserts; redone letter by letter in the
+                // (rare) case that one of them has a code longer than the 12-bit table
+                BitReader rd = src.rd;
+                uint32_t v[8];
+                uint32_t escape = 0;
+#pragma unroll
+                for (int j = 0; j < kGroup; j++) {
+                    rd.refill(c.sh.win);
+                    const uint32_t e = lds16(c.sh.lut + (rd.peek() << 1));
+                    escape |= e;
+                    rd.skip((e >> 8) & 0xFu);
+                    if ((j & 3) == 0) v[j >> 2] = e & 0xFFu;
+                    else if ((j & 3) == 1) v[j >> 2] = __byte_perm(v[j >> 2], e, 0x3240);
+                    else if ((j & 3) == 2) v[j >> 2] = __byte_perm(v[j >> 2], e, 0x3410);
+                    else v[j >> 2] = __byte_perm(v[j >> 2], e, 0x4210);
+                }
+                if (!(escape & 0x8000u)) {
+                    stg256(out + pos, v);
+                    src.rd = rd;
+                    done = true;
+                }
+            }
+            if (!done)
+                for (int j = 0; j < kGroup; j++) out[pos + j] = static_cast<uint8_t>(slow_next(src));
+            pos += kGroup;
+        }
+        for (; pos < hi; pos++) out[pos] = static_cast<uint8_t>(slow_next(src));   // ragged tail (end of output)
     }
 }
 

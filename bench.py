@@ -224,6 +224,35 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = n * world / (ms_per_step * 1e-3) / 1e9
 
+    # ---- secondary measurement: the GENERAL path (variable-length codes) on Zipf(1.2) bytes of the same size.
+    # configs[1] (uniform) yields a fixed-length code set and takes the table-translation fast path; this shows what
+    # the scan / self-synchronising kernels do.  Not part of `value`.
+    general = None
+    if args.workload == "uniform" and not args.no_general:
+        zdata = make_workload("zipf", n, rank * n, dev)
+        gphase = {k: 0.0 for k in phases}
+        gsteps = 3
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                codec.round_trip(zdata, comp_buf, out_buf)
+            stream.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            gm = [codec.round_trip(zdata, comp_buf, out_buf, want_events=True) for _ in range(gsteps)]
+            g1.record(stream)
+            stream.synchronize()
+        assert torch.equal(out_buf[:n], zdata), "general-path round trip mismatch"
+        for m in gm:
+            for k in phases:
+                gphase[k] += m[k][0].elapsed_time(m[k][1]) / gsteps
+        zc = codec.last_info["comp_len"]
+        general = {"workload": f"zipf(1.2) bytes, {n} B per GPU", "ms_per_step": g0.elapsed_time(g1) / gsteps,
+                   "comp_bytes": zc, "phase_ms": {k: round(v, 4) for k, v in gphase.items()},
+                   "alg_bytes": {"hist": n, "encode": n + zc, "dec_count": zc, "dec_write": zc + n}}
+        del zdata
+        codec.round_trip(data, comp_buf, out_buf)      # restore last_info for the headline workload
+        info = codec.last_info
+
     # ---- e2e through the host-buffer C ABI with pinned host memory
     from huff_encoding_b200 import api
     e2e_n = n
@@ -288,6 +317,16 @@ def run_ours(args):
                     "api": "hb_compress_u8 + hb_decompress_u8 (host buffers, pinned input)"},
             "gpu_launches": launches, "clocks": clocks,
         }
+        if general is not None:
+            gp = general["phase_ms"]
+            ga = general["alg_bytes"]
+            general["frac"] = {k: round(ga[k] / (gp[k] * 1e-3) / 1e9 / peak, 4) if gp[k] > 0 else None for k in gp}
+            cms, dms = gp["hist"] + gp["encode"], gp["dec_count"] + gp["dec_write"]
+            general["compress_gbs"] = n * world / (cms * 1e-3) / 1e9
+            general["decompress_gbs"] = n * world / (dms * 1e-3) / 1e9
+            general["compress_frac"] = round((2 * n + general["comp_bytes"]) / (cms * 1e-3) / 1e9 / peak, 4)
+            general["decompress_frac"] = round((n + general["comp_bytes"]) / (dms * 1e-3) / 1e9 / peak, 4)
+            line["general_path"] = general
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -302,6 +341,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="uniform", choices=["uniform", "zipf", "english"])
     ap.add_argument("--size", type=int, default=1 << 30, help="bytes per GPU")
+    ap.add_argument("--no-general", action="store_true", help="skip the secondary general-path (zipf) measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

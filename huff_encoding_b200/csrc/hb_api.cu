@@ -13,6 +13,7 @@
 
 #include "hb_decode.cuh"
 #include "hb_encode.cuh"
+#include "hb_fixed.cuh"
 #include "hb_hist.cuh"
 
 namespace {
@@ -86,6 +87,16 @@ struct hb_ctx {
     int enc_chunk = 4;                   // letters per chunk: 4 (codes <= 16 bits), 2 (<= 32), 1 (<= 64)
     unsigned long long *d_total_bits = nullptr;
 
+    // fixed-length fast path (hb_fixed.cuh)
+    bool fastpath = true;                // HB_NO_FASTPATH=1 turns it off (profiling the general path on uniform data)
+    uint8_t *d_fix_enc = nullptr;        // letter -> L-bit code
+    uint8_t *d_fix_dec = nullptr;        // L-bit pattern -> letter
+    uint32_t enc_fixed_len = 0, dec_fixed_len = 0;
+    int fix_grid = 0;
+    bool last_dec_fixed = false;
+    const uint8_t *last_fix_src = nullptr;
+    uint32_t last_fix_len = 0;
+
     // decoder
     hb::DecTables *d_dec_tables = nullptr;
     hb_tree dec_tree_cached;
@@ -123,6 +134,18 @@ bool same_nodes(const hb_tree &a, const hb_tree &b) {
     return a.n_nodes == b.n_nodes && a.root == b.root &&
            std::memcmp(a.nodes, b.nodes, sizeof(hb_node) * a.n_nodes) == 0;
 }
+
+// L if every code of the tree has length L in {1,2,4,8} (perfect tree or lone root), else 0
+uint32_t tree_fixed_len(const hb_tree *t) {
+    if (t->min_len != t->max_len) return 0;
+    const uint32_t L = t->max_len;
+    if (L != 1 && L != 2 && L != 4 && L != 8) return 0;
+    const bool lone_root = t->nodes[t->root].left == HB_NO_CHILD;
+    if (!lone_root && t->n_leaves != (1u << L)) return 0;
+    return L;
+}
+
+__global__ void set_u64_kernel(unsigned long long *p, unsigned long long v) { *p = v; }
 
 // ---------------------------------------------------------------- histogram
 size_t region_size_for(const hb_ctx *ctx, size_t n) {
@@ -185,6 +208,12 @@ hb_status upload_enc_table(hb_ctx *ctx, const hb_tree *tree) {
     ctx->enc_tree_cached = *tree;
     ctx->enc_tree_valid = true;
     ctx->enc_chunk = max_len <= 16 ? 4 : (max_len <= 32 ? 2 : 1);
+    ctx->enc_fixed_len = ctx->fastpath ? tree_fixed_len(tree) : 0;
+    if (ctx->enc_fixed_len) {
+        uint8_t codes[256];
+        for (int b = 0; b < 256; b++) codes[b] = tree->has_code[b] ? static_cast<uint8_t>(tree->code[b]) : 0;
+        HB_CUDA(cudaMemcpyAsync(ctx->d_fix_enc, codes, sizeof codes, cudaMemcpyHostToDevice, ctx->stream));
+    }
     return HB_OK;
 }
 
@@ -206,12 +235,35 @@ hb_status launch_encode_s(hb_ctx *ctx, const uint8_t *d_data, size_t n, uint32_t
 }
 
 hb_status launch_encode(hb_ctx *ctx, const uint8_t *d_data, size_t n, const hb_tree *tree, uint32_t start_bit,
-                        uint8_t *d_out, unsigned long long *d_total_bits) {
+                        uint8_t *d_out, unsigned long long *d_total_bits, bool all_coded) {
     if (n == 0) {
         if (d_total_bits) HB_CUDA(cudaMemsetAsync(d_total_bits, 0, sizeof(unsigned long long), ctx->stream));
         return HB_OK;
     }
     HB_TRY(upload_enc_table(ctx, tree));
+    const uint32_t L = ctx->enc_fixed_len;
+    if (L && all_coded && (start_bit % 8) == 0) {
+        // fixed-length code set: table translation, no offsets to scan
+        uint8_t *dst = d_out + start_bit / 8;
+        if (start_bit) HB_CUDA(cudaMemsetAsync(d_out, 0, start_bit / 8, ctx->stream));
+        if (L == 8 && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(d_data)) & 15) == 0) {
+            const size_t blocks = (n / 16 + hb::kFixThreads - 1) / hb::kFixThreads;
+            const int grid = static_cast<int>(std::max<size_t>(1, std::min<size_t>(ctx->fix_grid, blocks)));
+            hb::fixed8_translate_kernel<<<grid, hb::kFixThreads, 0, ctx->stream>>>(d_data, dst, n, ctx->d_fix_enc);
+        } else {
+            const size_t out_bytes = (n * L + 7) / 8;
+            const size_t blocks = (out_bytes + hb::kFixThreads - 1) / hb::kFixThreads;
+            const int grid = static_cast<int>(std::max<size_t>(1, std::min<size_t>(ctx->fix_grid * 4, blocks)));
+            hb::fixed_pack_kernel<<<grid, hb::kFixThreads, 0, ctx->stream>>>(d_data, n, dst, out_bytes, L, ctx->d_fix_enc);
+        }
+        ctx->launches++;
+        HB_CUDA(cudaGetLastError());
+        if (d_total_bits) {
+            set_u64_kernel<<<1, 1, 0, ctx->stream>>>(d_total_bits, static_cast<unsigned long long>(n) * L);
+            ctx->launches++;
+        }
+        return HB_OK;
+    }
     switch (ctx->enc_chunk) {
         case 4: return launch_encode_s<4>(ctx, d_data, n, start_bit, d_out, d_total_bits);
         case 2: return launch_encode_s<2>(ctx, d_data, n, start_bit, d_out, d_total_bits);
@@ -282,6 +334,18 @@ hb_status upload_dec_tables(hb_ctx *ctx, const hb_tree *tree) {
     HB_CUDA(cudaStreamSynchronize(ctx->stream));       // `t` is reused by the next call
     ctx->dec_tree_cached = *tree;
     ctx->dec_tree_valid = true;
+    ctx->dec_fixed_len = ctx->fastpath ? tree_fixed_len(tree) : 0;
+    if (ctx->dec_fixed_len) {
+        const uint32_t L = ctx->dec_fixed_len;
+        uint8_t letters[256] = {0};
+        for (uint32_t pat = 0; pat < (1u << L); pat++) {                  // walk the pattern down the tree
+            uint32_t node = tree->root;
+            for (uint32_t k = 0; k < L && tree->nodes[node].left != HB_NO_CHILD; k++)
+                node = ((pat >> (L - 1 - k)) & 1) ? tree->nodes[node].right : tree->nodes[node].left;
+            letters[pat] = tree->nodes[node].letter;
+        }
+        HB_CUDA(cudaMemcpyAsync(ctx->d_fix_dec, letters, sizeof letters, cudaMemcpyHostToDevice, ctx->stream));
+    }
     return HB_OK;
 }
 
@@ -307,6 +371,24 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
         return HB_OK;
     }
     HB_TRY(upload_dec_tables(ctx, tree));
+    ctx->last_dec_fixed = false;
+    if (ctx->dec_fixed_len && entry_bit >= 0 && (entry_bit % 8) == 0 && static_cast<uint64_t>(entry_bit) >= own_begin) {
+        // fixed-length code set: every L-th bit after the entry starts a code word; nothing to count on the device
+        const uint64_t L = ctx->dec_fixed_len, e = static_cast<uint64_t>(entry_bit);
+        const uint64_t by_own = own_end > e ? (own_end - e + L - 1) / L : 0;
+        const uint64_t by_avail = avail_bits > e ? (avail_bits - e) / L : 0;
+        const uint64_t n = std::min(by_own, by_avail);
+        info->entry_bit = entry_bit;
+        info->exit_bit = (n == by_own) ? e + n * L : avail_bits;         // same convention as the general path
+        info->n_letters = n;
+        ctx->last_dec_fixed = true;
+        ctx->last_fix_src = d_buf + e / 8;
+        ctx->last_fix_len = static_cast<uint32_t>(L);
+        ctx->last_dec_total = n;
+        ctx->last_dec.n_blocks = 0;
+        ctx->last_dec_valid = true;
+        return HB_OK;
+    }
     const uint64_t chunk_bits = static_cast<uint64_t>(hb::kChunkWords) * 32;
     const uint64_t first_block = own_begin / chunk_bits;
     const uint64_t last_block = (own_end - 1) / chunk_bits;
@@ -376,7 +458,25 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
 hb_status run_write_pass(hb_ctx *ctx, uint8_t *d_out, size_t out_cap) {
     if (!ctx->last_dec_valid) return HB_ERR_INVALID_ARG;
     if (ctx->last_dec_total > out_cap) return HB_ERR_CAPACITY;
-    if (ctx->last_dec_total == 0 || ctx->last_dec.n_blocks == 0) return HB_OK;
+    if (ctx->last_dec_total == 0) return HB_OK;
+    if (ctx->last_dec_fixed) {
+        const size_t n = static_cast<size_t>(ctx->last_dec_total);
+        const uint32_t L = ctx->last_fix_len;
+        if (L == 8 && ((reinterpret_cast<uintptr_t>(ctx->last_fix_src) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0) {
+            const size_t blocks = (n / 16 + hb::kFixThreads - 1) / hb::kFixThreads;
+            const int grid = static_cast<int>(std::max<size_t>(1, std::min<size_t>(ctx->fix_grid, blocks)));
+            hb::fixed8_translate_kernel<<<grid, hb::kFixThreads, 0, ctx->stream>>>(ctx->last_fix_src, d_out, n, ctx->d_fix_dec);
+        } else {
+            const size_t n_bytes = (n * L + 7) / 8;
+            const size_t blocks = (n_bytes + hb::kFixThreads - 1) / hb::kFixThreads;
+            const int grid = static_cast<int>(std::max<size_t>(1, std::min<size_t>(ctx->fix_grid * 4, blocks)));
+            hb::fixed_unpack_kernel<<<grid, hb::kFixThreads, 0, ctx->stream>>>(ctx->last_fix_src, d_out, n, L, ctx->d_fix_dec);
+        }
+        ctx->launches++;
+        HB_CUDA(cudaGetLastError());
+        return HB_OK;
+    }
+    if (ctx->last_dec.n_blocks == 0) return HB_OK;
     const hb::DecParams &p = ctx->last_dec;
     const int grid = static_cast<int>(std::min<uint32_t>(ctx->dec_write_grid, p.n_blocks));
     hb::dec_write_kernel<<<grid, hb::kDecThreads, hb::kDecSmemWrite, ctx->stream>>>(
@@ -439,6 +539,9 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
         HB_CUDA(cudaMalloc(&ctx->d_enc_table, sizeof(hb::EncTable)));
         HB_CUDA(cudaMalloc(&ctx->d_total_bits, sizeof(unsigned long long)));
         HB_CUDA(cudaMalloc(&ctx->d_dec_tables, sizeof(hb::DecTables)));
+        HB_CUDA(cudaMalloc(&ctx->d_fix_enc, 256));
+        HB_CUDA(cudaMalloc(&ctx->d_fix_dec, 256));
+        { const char *nf = std::getenv("HB_NO_FASTPATH"); ctx->fastpath = !(nf && nf[0] == '1'); }
         HB_CUDA(cudaMalloc(&ctx->d_dec_result, sizeof(DecResult)));
         HB_CUDA(cudaMalloc(&ctx->d_n_dirty, sizeof(uint32_t)));
         HB_CUDA(cudaMallocHost(&ctx->h_dec_result, sizeof(DecResult)));
@@ -451,6 +554,8 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
         HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::hist_lane_columns_kernel, hb::kHistThreads, 0));
         ctx->hist_ctas_per_sm = std::max(occ, 1);
         ctx->hist_grid = ctx->sm_count * ctx->hist_ctas_per_sm;
+        HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::fixed8_translate_kernel, hb::kFixThreads, 0));
+        ctx->fix_grid = ctx->sm_count * std::max(occ, 1);
         HB_CUDA(cudaFuncSetAttribute(hb::encode_regions_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::enc_smem_bytes(4))));
         HB_CUDA(cudaFuncSetAttribute(hb::encode_regions_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::enc_smem_bytes(2))));
         HB_CUDA(cudaFuncSetAttribute(hb::encode_regions_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::enc_smem_bytes(1))));
@@ -469,7 +574,7 @@ hb_status hb_ctx_destroy(hb_ctx *ctx) {
     if (!ctx) return HB_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_hist); cudaFree(ctx->d_region_hist); cudaFree(ctx->d_enc_table); cudaFree(ctx->d_total_bits); cudaFree(ctx->d_dec_tables);
+    cudaFree(ctx->d_hist); cudaFree(ctx->d_region_hist); cudaFree(ctx->d_enc_table); cudaFree(ctx->d_total_bits); cudaFree(ctx->d_dec_tables); cudaFree(ctx->d_fix_enc); cudaFree(ctx->d_fix_dec);
     cudaFree(ctx->d_dec_result); cudaFree(ctx->d_n_dirty);
     if (ctx->h_dec_result) cudaFreeHost(ctx->h_dec_result);
     if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
@@ -518,7 +623,9 @@ hb_status hb_encode_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, const h
     if (!tree || !d_out || (n && !d_data) || start_bit > 31) return HB_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(d_data) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 3)) return HB_ERR_INVALID_ARG;
     (void)out_cap;   // capacity is the caller's contract (exact size comes from hb_stream_bits); checked in the *_u8 path
-    return launch_encode(ctx, d_data, n, tree, start_bit, d_out, reinterpret_cast<unsigned long long *>(d_total_bits));
+    bool all_coded = true;
+    for (int b = 0; b < 256; b++) all_coded = all_coded && tree->has_code[b];
+    return launch_encode(ctx, d_data, n, tree, start_bit, d_out, reinterpret_cast<unsigned long long *>(d_total_bits), all_coded);
 }
 
 hb_status hb_compress_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, int order_mode, hb_tree *tree_out,
@@ -536,7 +643,7 @@ hb_status hb_compress_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, int o
     HB_TRY(check_encodable(ctx->h_hist, tree_out, &bits, &missing));
     const size_t need = static_cast<size_t>((bits + 7) / 8);
     if (((need + 3) & ~static_cast<size_t>(3)) > out_cap) { *comp_len = need; return HB_ERR_CAPACITY; }
-    HB_TRY(launch_encode(ctx, d_data, n, tree_out, 0, d_out, nullptr));
+    HB_TRY(launch_encode(ctx, d_data, n, tree_out, 0, d_out, nullptr, true));
     *comp_len = need;
     *padding_bits = static_cast<uint8_t>((8 - bits % 8) % 8);    // comp.rs:446
     return HB_OK;
@@ -617,7 +724,7 @@ static hb_status compress_host_common(hb_ctx *ctx, const uint8_t *data, size_t n
     if (bits == 0) return HB_ERR_EMPTY_COMP;                      // comp.rs:450 -> :56-58 (n == 0 with a given tree)
     const size_t need = static_cast<size_t>((bits + 7) / 8);
     HB_TRY(ctx->stage_out.reserve(need + 16));
-    HB_TRY(launch_encode(ctx, ctx->stage_in.p, n, tree, 0, ctx->stage_out.p, nullptr));
+    HB_TRY(launch_encode(ctx, ctx->stage_in.p, n, tree, 0, ctx->stage_out.p, nullptr, true));
     uint8_t *host = static_cast<uint8_t *>(std::malloc(need));
     if (!host) return HB_ERR_NO_MEM;
     cudaError_t e = cudaMemcpyAsync(host, ctx->stage_out.p, need, cudaMemcpyDeviceToHost, ctx->stream);

@@ -205,13 +205,46 @@ __device__ __forceinline__ void dec_load_tables(const DecTables *__restrict__ t,
 }
 
 // Stage window words [chunk*8192 - 32, chunk*8192 + 8192 + 32) of the stream into padded shared memory, MSB-first.
+// All global loads of a thread are issued before the first dependent use (9 x 128-bit in flight per thread).
 __device__ __forceinline__ void dec_load_window(const DecParams &p, uint32_t chunk, uint32_t *win) {
     const long long w_begin = static_cast<long long>(chunk) * kChunkWords - kHaloWords;
-    for (int i = threadIdx.x; i < kWinWords; i += blockDim.x) {
-        const long long gw = w_begin + i;
-        uint32_t v = 0;
-        if (gw >= 0 && static_cast<uint64_t>(gw) < p.n_words_readable) v = bswap32(ld_stream_u32(p.words + gw));
-        win[i + (i >> 5)] = v;
+    constexpr int kVecs = kWinWords / 4;                                   // 2064 uint4
+    constexpr int kPerThread = (kVecs + kDecThreads - 1) / kDecThreads;    // 9
+    if ((reinterpret_cast<uintptr_t>(p.words) & 15) == 0) {
+        uint4 v[kPerThread];
+#pragma unroll
+        for (int k = 0; k < kPerThread; k++) {
+            const int i4 = threadIdx.x + k * kDecThreads;
+            const long long gw = w_begin + 4ll * i4;
+            v[k] = make_uint4(0, 0, 0, 0);
+            if (i4 < kVecs && gw >= 0 && static_cast<uint64_t>(gw) < p.n_words_readable)
+                v[k] = ld_stream_u4(reinterpret_cast<const uint4 *>(p.words + gw));
+        }
+#pragma unroll
+        for (int k = 0; k < kPerThread; k++) {
+            const int i4 = threadIdx.x + k * kDecThreads;
+            if (i4 < kVecs) {
+                const int i = 4 * i4;
+                uint32_t *dst = win + i + (i >> 5);                        // the 4 words share a row: contiguous
+                dst[0] = bswap32(v[k].x); dst[1] = bswap32(v[k].y); dst[2] = bswap32(v[k].z); dst[3] = bswap32(v[k].w);
+            }
+        }
+    } else {
+        for (int base = 0; base < kWinWords; base += 8 * kDecThreads) {
+            uint32_t v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int i = base + threadIdx.x + k * kDecThreads;
+                const long long gw = w_begin + i;
+                v[k] = 0;
+                if (i < kWinWords && gw >= 0 && static_cast<uint64_t>(gw) < p.n_words_readable) v[k] = ld_stream_u32(p.words + gw);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int i = base + threadIdx.x + k * kDecThreads;
+                if (i < kWinWords) win[i + (i >> 5)] = bswap32(v[k]);
+            }
+        }
     }
     if (threadIdx.x < 3) win[kWinWords + (kWinWords >> 5) + threadIdx.x] = 0;   // look-ahead slack past the window
 }

@@ -132,6 +132,36 @@ def test_eight_equal_symbols_three_bit_codes_do_not_self_synchronise(hb):
     assert set(len(c) for c in cd.huff_tree().read_codes().values()) == {3}
 
 
+@pytest.mark.parametrize("mask,L", [(3, 2), (15, 4), (255, 8)])
+@pytest.mark.parametrize("n", [1_000_003, 4096 * 3, 17])
+def test_fixed_length_code_sets_fast_path(hb, mask, L, n):
+    # equiprobable 2^L letters -> perfect tree, every code L bits: the table-translation fast path (hb_fixed.cuh)
+    base = np.tile(np.arange(mask + 1, dtype=np.uint8), 4)                 # make sure every letter is present
+    data = np.concatenate([base, (G.uniform(n, seed=L) & mask).astype(np.uint8)]) * (255 // mask)
+    if n == 17:
+        data = np.tile(np.arange(mask + 1, dtype=np.uint8), 3)[: max(17, mask + 1) + 2 * (mask + 1)] * (255 // mask)
+    cd = _assert_compress_parity(hb, data)
+    lens = set(len(c) for c in cd.huff_tree().read_codes().values())
+    if len(lens) == 1:
+        assert lens == {L}
+
+
+def test_general_path_on_uniform_when_fast_path_is_disabled(hb):
+    import os
+    os.environ["HB_NO_FASTPATH"] = "1"
+    try:
+        ctx = hb.Context(0)
+    finally:
+        del os.environ["HB_NO_FASTPATH"]
+    data = G.uniform((2 << 20) + 77)
+    cd = hb.compress(data, ctx=ctx)
+    comp, pad, tree = O.compress(data)
+    assert set(tree.lens()) == {8}
+    assert cd.padding_bits() == pad and np.array_equal(cd.comp_bytes(), comp)
+    assert np.array_equal(hb.decompress(cd, ctx=ctx), data)
+    ctx.close()
+
+
 def test_lengths_with_common_factor(hb):
     # weights 4,4,4,1,1,1,1 -> lengths {2,2,2,4,4,4,4}: gcd 2 but not fixed length
     rng = np.random.default_rng(3)

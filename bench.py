@@ -39,48 +39,100 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-# ---------------------------------------------------------------- clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------- clocks sampler (NVML polled during the timed region)
 class ClockSampler:
+    """Polls SM clock + clock-event reasons every ~2 ms from a thread (NVML); falls back to `nvidia-smi -lms`."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.samples, self.proc = index, [], None
+    def __init__(self, index: int, uuid: str | None = None):
+        self.index, self.uuid = index, uuid
+        self.sm, self.mask, self.max_mhz = [], 0, None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+        self._smi = None
+        self._smi_lines = []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid.encode() if hasattr(self.uuid, "encode") else self.uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self._nvml = (pynvml, h, reasons_fn)
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+            return
         except Exception:
-            self.proc = None
+            self._nvml = None
+        try:
+            self._smi = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "10"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._thread = threading.Thread(target=self._read_smi, daemon=True)
+            self._thread.start()
+        except Exception:
+            self._smi = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append(line.strip())
+    def _poll(self):
+        pynvml, h, reasons_fn = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                self.mask |= int(reasons_fn(h))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _read_smi(self):
+        for line in self._smi.stdout:
+            self._smi_lines.append(line.strip())
+
+    def clear(self):
+        self.sm.clear()
+        self.mask = 0
+        self._smi_lines.clear()
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            parts = [x.strip() for x in s.split(",")]
-            if len(parts) < 6:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx = float(parts[1])
-            except ValueError:
-                continue
-            for nm, v in zip(names, parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self._stop.set()
+        if self._smi is not None:
+            self._smi.terminate()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = set()
+            for s in self._smi_lines:
+                parts = [x.strip() for x in s.split(",")]
+                if len(parts) < 6:
+                    continue
+                try:
+                    self.sm.append(float(parts[0]))
+                    self.max_mhz = float(parts[1])
+                except ValueError:
+                    continue
+                for nm, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+                    "samples": len(sm), "source": "nvidia-smi"}
+        if self._nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+        sm = sorted(self.sm)
+        reasons = sorted(nm for bit, nm in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "source": "nvml"}
 
 
 # ---------------------------------------------------------------- workloads
@@ -182,16 +234,20 @@ def run_ours(args):
         return marks
 
     with torch.cuda.stream(stream):
-        sampler = ClockSampler(local_rank)
+        try:
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+        except Exception:
+            uuid = None
+        sampler = ClockSampler(local_rank, uuid)
         sampler.start()
-        time.sleep(0.3)                      # let nvidia-smi come up; its samples then cover warm-up + timed region
+        time.sleep(0.05)
         for _ in range(args.warmup):
             step(False)
         stream.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler.samples.clear()              # keep only samples taken during the timed region
+        sampler.clear()                      # keep only samples taken during the timed region
         launches0 = eng.kernel_launches()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         all_marks = []
@@ -258,18 +314,20 @@ def run_ours(args):
     e2e_n = n
     host_in = torch.empty(e2e_n, dtype=torch.uint8, pin_memory=True)
     host_in.copy_(data[:e2e_n])
-    h_np = host_in.numpy()
-    e2e_steps = max(1, min(args.steps, 3))
-    cd = api.compress(h_np, ctx=eng.ctx)          # warm-up (buffers, tables)
-    _ = api.decompress(cd, ctx=eng.ctx)
+    host_comp = torch.empty(e2e_n + e2e_n // 8 + 4096, dtype=torch.uint8, pin_memory=True)
+    host_out = torch.empty(e2e_n + 64, dtype=torch.uint8, pin_memory=True)
+    h_np, c_np, o_np = host_in.numpy(), host_comp.numpy(), host_out.numpy()
+    e2e_steps = max(1, min(args.steps, 5))
+    cd = api.compress(h_np, ctx=eng.ctx, out=c_np)          # warm-up (device staging buffers, tables)
+    _ = api.decompress(cd, ctx=eng.ctx, out=o_np)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        cd = api.compress(h_np, ctx=eng.ctx)
-        back = api.decompress(cd, ctx=eng.ctx)
+        cd = api.compress(h_np, ctx=eng.ctx, out=c_np)      # H2D of the letters + D2H of the stream inside
+        back = api.decompress(cd, ctx=eng.ctx, out=o_np)    # H2D of the stream + D2H of the letters inside
     e2e_dt = (time.perf_counter() - t0) / e2e_steps
-    assert back.size == e2e_n and np.array_equal(back[:65536], h_np[:65536])
+    assert back.size == e2e_n and np.array_equal(back[:65536], h_np[:65536]) and np.array_equal(back[-4096:], h_np[-4096:])
     clen = int(cd.comp_bytes().size)
     t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
     if world > 1:
@@ -281,13 +339,17 @@ def run_ours(args):
         c_bytes = info["comp_len"]
         algo = {"hist": n, "encode": n + c_bytes, "dec_count": c_bytes, "dec_write": c_bytes + n}
         kern = {}
+        fixed = info.get("fixed_len", 0)
         for k in phases:
             ms = phase_ms[k]
-            kern[k] = {"ms": round(ms, 4), "algorithmic_bytes": algo[k],
-                       "achieved_gbs": round(algo[k] / (ms * 1e-3) / 1e9, 1) if ms > 0 else None,
-                       "frac": round(algo[k] / (ms * 1e-3) / 1e9 / peak, 4) if ms > 0 else None}
+            host_only = (k == "dec_count" and fixed)    # fixed-length code set: the count is host arithmetic, no kernel
+            kern[k] = {"ms": round(ms, 4), "algorithmic_bytes": 0 if host_only else algo[k],
+                       "achieved_gbs": round(algo[k] / (ms * 1e-3) / 1e9, 1) if ms > 0 and not host_only else None,
+                       "frac": round(algo[k] / (ms * 1e-3) / 1e9 / peak, 4) if ms > 0 and not host_only else None}
+            if host_only:
+                kern[k]["note"] = "no kernel: fixed-length code set, letter count = bits / L on the host"
         # the dominant kernel = the largest share of the step; decode is reported as count+write against C+N
-        dom = max(phases, key=lambda k: phase_ms[k])
+        dom = max([k for k in phases if kern[k]["frac"] is not None], key=lambda k: phase_ms[k])
         dec_ms = phase_ms["dec_count"] + phase_ms["dec_write"]
         comp_ms = phase_ms["hist"] + phase_ms["encode"]
         roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
@@ -314,7 +376,7 @@ def run_ours(args):
                              if cpu_v is not None else None),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_n + clen,
                     "d2h_bytes_per_step": clen + e2e_n, "steps": e2e_steps,
-                    "api": "hb_compress_u8 + hb_decompress_u8 (host buffers, pinned input)"},
+                    "api": "hb_compress_u8_into + hb_decompress_u8_into (pinned host buffers in and out)"},
             "gpu_launches": launches, "clocks": clocks,
         }
         if general is not None:

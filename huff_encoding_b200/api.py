@@ -384,12 +384,18 @@ def _take(ptr: C.c_void_p, n: int) -> np.ndarray:
     return out
 
 
-def compress(letters, ctx: Context | None = None) -> CompressData:
-    """comp.rs:353-356"""
+def compress(letters, ctx: Context | None = None, out: np.ndarray | None = None) -> CompressData:
+    """comp.rs:353-356.  `out`: optional caller-owned u8 buffer (e.g. pinned memory reused across calls) that
+    receives comp_bytes; the returned CompressData then views it."""
     a = _u8(letters)
     ctx = ctx or default_context()
     t = L.HbTree()
-    ptr, n, pad = C.c_void_p(), C.c_size_t(0), C.c_uint8(0)
+    n, pad = C.c_size_t(0), C.c_uint8(0)
+    if out is not None:
+        _raise(L.load().hb_compress_u8_into(ctx.handle, a.ctypes.data, a.size, L.HB_ORDER_ASC, C.byref(t),
+                                            out.ctypes.data, out.size, C.byref(n), C.byref(pad)))
+        return CompressData(out[: n.value], pad.value, HuffTree(t))
+    ptr = C.c_void_p()
     _raise(L.load().hb_compress_u8(ctx.handle, a.ctypes.data, a.size, L.HB_ORDER_ASC, C.byref(t),
                                    C.byref(ptr), C.byref(n), C.byref(pad)))
     return CompressData(_take(ptr, n.value), pad.value, HuffTree(t))
@@ -406,11 +412,16 @@ def compress_with_tree(letters, huff_tree: HuffTree, ctx: Context | None = None)
     return CompressData(_take(ptr, n.value), pad.value, huff_tree)
 
 
-def decompress(comp_data: CompressData, ctx: Context | None = None) -> np.ndarray:
-    """comp.rs:487-519"""
+def decompress(comp_data: CompressData, ctx: Context | None = None, out: np.ndarray | None = None) -> np.ndarray:
+    """comp.rs:487-519.  `out`: optional caller-owned u8 buffer that receives the letters."""
     ctx = ctx or default_context()
     cb = comp_data.comp_bytes()
-    ptr, n = C.c_void_p(), C.c_size_t(0)
+    n = C.c_size_t(0)
+    if out is not None:
+        _raise(L.load().hb_decompress_u8_into(ctx.handle, cb.ctypes.data, cb.size, comp_data.padding_bits(),
+                                              C.byref(comp_data.huff_tree().raw), out.ctypes.data, out.size, C.byref(n)))
+        return out[: n.value]
+    ptr = C.c_void_p()
     _raise(L.load().hb_decompress_u8(ctx.handle, cb.ctypes.data, cb.size, comp_data.padding_bits(),
                                      C.byref(comp_data.huff_tree().raw), C.byref(ptr), C.byref(n)))
     return _take(ptr, n.value)

@@ -694,10 +694,11 @@ hb_status hb_histogram_u8(hb_ctx *ctx, const uint8_t *data, size_t n, uint64_t o
     return HB_OK;
 }
 
+// dst == nullptr: allocate the result with malloc (returned through *comp_bytes); else write into dst[0..cap)
 static hb_status compress_host_common(hb_ctx *ctx, const uint8_t *data, size_t n, const hb_tree *tree, int order_mode,
-                                      hb_tree *tree_out, uint8_t **comp_bytes, size_t *comp_len, uint8_t *padding_bits,
-                                      uint8_t *missing) {
-    *comp_bytes = nullptr;
+                                      hb_tree *tree_out, uint8_t **comp_bytes, uint8_t *dst, size_t cap, size_t *comp_len,
+                                      uint8_t *padding_bits, uint8_t *missing) {
+    if (comp_bytes) *comp_bytes = nullptr;
     *comp_len = 0;
     HB_TRY(ctx->stage_in.reserve(n + 16));
     if (n) HB_CUDA(cudaMemcpyAsync(ctx->stage_in.p, data, n, cudaMemcpyHostToDevice, ctx->stream));
@@ -723,14 +724,15 @@ static hb_status compress_host_common(hb_ctx *ctx, const uint8_t *data, size_t n
         if (ctx->h_hist[b] && tree->code_len[b] > HB_MAX_ENCODE_BITS) return HB_ERR_CODE_TOO_LONG;
     if (bits == 0) return HB_ERR_EMPTY_COMP;                      // comp.rs:450 -> :56-58 (n == 0 with a given tree)
     const size_t need = static_cast<size_t>((bits + 7) / 8);
+    if (dst && need > cap) { *comp_len = need; return HB_ERR_CAPACITY; }
     HB_TRY(ctx->stage_out.reserve(need + 16));
     HB_TRY(launch_encode(ctx, ctx->stage_in.p, n, tree, 0, ctx->stage_out.p, nullptr, true));
-    uint8_t *host = static_cast<uint8_t *>(std::malloc(need));
+    uint8_t *host = dst ? dst : static_cast<uint8_t *>(std::malloc(need));
     if (!host) return HB_ERR_NO_MEM;
     cudaError_t e = cudaMemcpyAsync(host, ctx->stage_out.p, need, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { std::free(host); return cuda_fail(e, "D2H of the compressed stream", __LINE__); }
-    *comp_bytes = host;
+    if (e != cudaSuccess) { if (!dst) std::free(host); return cuda_fail(e, "D2H of the compressed stream", __LINE__); }
+    if (comp_bytes) *comp_bytes = host;
     *comp_len = need;
     *padding_bits = static_cast<uint8_t>((8 - bits % 8) % 8);
     return HB_OK;
@@ -741,7 +743,7 @@ hb_status hb_compress_u8(hb_ctx *ctx, const uint8_t *data, size_t n, int order_m
     HB_TRY(check_ctx(ctx));
     if (!tree_out || !comp_bytes || !comp_len || !padding_bits || (n && !data)) return HB_ERR_INVALID_ARG;
     if (n == 0) return HB_ERR_EMPTY_WEIGHTS;
-    return compress_host_common(ctx, data, n, nullptr, order_mode, tree_out, comp_bytes, comp_len, padding_bits, nullptr);
+    return compress_host_common(ctx, data, n, nullptr, order_mode, tree_out, comp_bytes, nullptr, 0, comp_len, padding_bits, nullptr);
 }
 
 hb_status hb_compress_with_tree_u8(hb_ctx *ctx, const uint8_t *data, size_t n, const hb_tree *tree,
@@ -749,14 +751,12 @@ hb_status hb_compress_with_tree_u8(hb_ctx *ctx, const uint8_t *data, size_t n, c
     HB_TRY(check_ctx(ctx));
     if (!tree || !comp_bytes || !comp_len || !padding_bits || (n && !data)) return HB_ERR_INVALID_ARG;
     if (n == 0) return HB_ERR_EMPTY_COMP;                         // empty letters -> CompressData::new panics (comp.rs:56-58)
-    return compress_host_common(ctx, data, n, tree, 0, nullptr, comp_bytes, comp_len, padding_bits, missing);
+    return compress_host_common(ctx, data, n, tree, 0, nullptr, comp_bytes, nullptr, 0, comp_len, padding_bits, missing);
 }
 
-hb_status hb_decompress_u8(hb_ctx *ctx, const uint8_t *comp, size_t comp_len, uint8_t padding_bits,
-                           const hb_tree *tree, uint8_t **out, size_t *out_n) {
-    HB_TRY(check_ctx(ctx));
-    if (!tree || !out || !out_n) return HB_ERR_INVALID_ARG;
-    *out = nullptr;
+static hb_status decompress_host_common(hb_ctx *ctx, const uint8_t *comp, size_t comp_len, uint8_t padding_bits,
+                                        const hb_tree *tree, uint8_t **out, uint8_t *dst, size_t cap, size_t *out_n) {
+    if (out) *out = nullptr;
     *out_n = 0;
     if (comp_len == 0) return HB_ERR_EMPTY_COMP;
     if (padding_bits > 7) return HB_ERR_BAD_PADDING;
@@ -767,19 +767,51 @@ hb_status hb_decompress_u8(hb_ctx *ctx, const uint8_t *comp, size_t comp_len, ui
     hb_shard_info info;
     HB_TRY(run_count_pass(ctx, ctx->stage_in.p, total_bits, 0, total_bits, 0, 0, tree, &info));
     const size_t n = static_cast<size_t>(info.n_letters);
-    uint8_t *host = static_cast<uint8_t *>(std::malloc(n ? n : 1));
+    if (dst && n > cap) { *out_n = n; return HB_ERR_CAPACITY; }
+    uint8_t *host = dst ? dst : static_cast<uint8_t *>(std::malloc(n ? n : 1));
     if (!host) return HB_ERR_NO_MEM;
     if (n) {
-        hb_status rc = ctx->stage_out.reserve(n + 16);
+        hb_status rc = ctx->stage_out.reserve(n + 64);
         if (rc == HB_OK) rc = run_write_pass(ctx, ctx->stage_out.p, n);
-        if (rc != HB_OK) { std::free(host); return rc; }
+        if (rc != HB_OK) { if (!dst) std::free(host); return rc; }
         cudaError_t e = cudaMemcpyAsync(host, ctx->stage_out.p, n, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { std::free(host); return cuda_fail(e, "D2H of the decoded letters", __LINE__); }
+        if (e != cudaSuccess) { if (!dst) std::free(host); return cuda_fail(e, "D2H of the decoded letters", __LINE__); }
     }
-    *out = host;
+    if (out) *out = host;
     *out_n = n;
     return HB_OK;
+}
+
+hb_status hb_decompress_u8(hb_ctx *ctx, const uint8_t *comp, size_t comp_len, uint8_t padding_bits,
+                           const hb_tree *tree, uint8_t **out, size_t *out_n) {
+    HB_TRY(check_ctx(ctx));
+    if (!tree || !out || !out_n) return HB_ERR_INVALID_ARG;
+    return decompress_host_common(ctx, comp, comp_len, padding_bits, tree, out, nullptr, 0, out_n);
+}
+
+hb_status hb_decompress_u8_into(hb_ctx *ctx, const uint8_t *comp, size_t comp_len, uint8_t padding_bits,
+                                const hb_tree *tree, uint8_t *out, size_t out_cap, size_t *out_n) {
+    HB_TRY(check_ctx(ctx));
+    if (!tree || !out || !out_n) return HB_ERR_INVALID_ARG;
+    return decompress_host_common(ctx, comp, comp_len, padding_bits, tree, nullptr, out, out_cap, out_n);
+}
+
+hb_status hb_compress_u8_into(hb_ctx *ctx, const uint8_t *data, size_t n, int order_mode, hb_tree *tree_out,
+                              uint8_t *comp_bytes, size_t comp_cap, size_t *comp_len, uint8_t *padding_bits) {
+    HB_TRY(check_ctx(ctx));
+    if (!tree_out || !comp_bytes || !comp_len || !padding_bits || (n && !data)) return HB_ERR_INVALID_ARG;
+    if (n == 0) return HB_ERR_EMPTY_WEIGHTS;
+    return compress_host_common(ctx, data, n, nullptr, order_mode, tree_out, nullptr, comp_bytes, comp_cap, comp_len, padding_bits, nullptr);
+}
+
+hb_status hb_compress_with_tree_u8_into(hb_ctx *ctx, const uint8_t *data, size_t n, const hb_tree *tree,
+                                        uint8_t *comp_bytes, size_t comp_cap, size_t *comp_len, uint8_t *padding_bits,
+                                        uint8_t *missing) {
+    HB_TRY(check_ctx(ctx));
+    if (!tree || !comp_bytes || !comp_len || !padding_bits || (n && !data)) return HB_ERR_INVALID_ARG;
+    if (n == 0) return HB_ERR_EMPTY_COMP;
+    return compress_host_common(ctx, data, n, tree, 0, nullptr, nullptr, comp_bytes, comp_cap, comp_len, padding_bits, missing);
 }
 
 }  // extern "C"

@@ -56,8 +56,9 @@ class ShardedCodec:
         my_bits = int((local_w * lens).sum())
         if self.world > 1:
             self._mine[0] = my_bits
-            dist.all_gather_into_tensor(self._bits, self._mine)
-            all_bits = [int(x) for x in self._bits.cpu().tolist()]
+            parts = [torch.zeros_like(self._mine) for _ in range(self.world)]
+            dist.all_gather(parts, self._mine)
+            all_bits = [int(x.item()) for x in parts]
         else:
             all_bits = [my_bits]
         offset = sum(all_bits[: self.rank])
@@ -71,7 +72,9 @@ class ShardedCodec:
         eng.encode(data, tree, comp_buf, start_bit=start_bit)
         if marks is not None:
             marks["encode"] = (a, self._event())
-        info = {"tree": tree, "bits": my_bits, "bit_offset": offset, "start_bit": start_bit, "comp_len": comp_len,
+        raw = tree.raw
+        fixed = raw.max_len if (raw.min_len == raw.max_len and raw.max_len in (1, 2, 4, 8)) else 0
+        info = {"fixed_len": fixed, "tree": tree, "bits": my_bits, "bit_offset": offset, "start_bit": start_bit, "comp_len": comp_len,
                 "total_bits": total, "padding_bits": (8 - total % 8) % 8, "all_bits": all_bits}
         self.last_info = info
         return info
@@ -142,9 +145,9 @@ class ShardedCodec:
         if self.world > 1:
             for _ in range(self.world):                     # a refuted entry can cascade at most world-1 times
                 trip = torch.tensor([e + bit0, x + bit0, n], dtype=torch.int64, device=buf.device)
-                allt = torch.zeros(self.world * 3, dtype=torch.int64, device=buf.device)
-                dist.all_gather_into_tensor(allt, trip)
-                t = allt.cpu().view(self.world, 3)
+                parts = [torch.zeros_like(trip) for _ in range(self.world)]
+                dist.all_gather(parts, trip)
+                t = torch.stack(parts).cpu()
                 bad = [g for g in range(1, self.world) if int(t[g, 0]) != int(t[g - 1, 1])]
                 if not bad:
                     break

@@ -123,6 +123,17 @@ hb_status hb_compress_with_tree_u8(hb_ctx *ctx, const uint8_t *data, size_t n, c
 hb_status hb_decompress_u8(hb_ctx *ctx, const uint8_t *comp, size_t comp_len, uint8_t padding_bits,
                            const hb_tree *tree, uint8_t **out, size_t *out_n);
 
+/* Same three calls writing into CALLER-OWNED host buffers (e.g. pinned memory that is reused across calls, which
+ * is what makes the host path run at PCIe speed).  If the buffer is too small they return HB_ERR_CAPACITY and
+ * report the needed size in *comp_len / *out_n. */
+hb_status hb_compress_u8_into(hb_ctx *ctx, const uint8_t *data, size_t n, int order_mode, hb_tree *tree_out,
+                              uint8_t *comp_bytes, size_t comp_cap, size_t *comp_len, uint8_t *padding_bits);
+hb_status hb_compress_with_tree_u8_into(hb_ctx *ctx, const uint8_t *data, size_t n, const hb_tree *tree,
+                                        uint8_t *comp_bytes, size_t comp_cap, size_t *comp_len, uint8_t *padding_bits,
+                                        uint8_t *missing);
+hb_status hb_decompress_u8_into(hb_ctx *ctx, const uint8_t *comp, size_t comp_len, uint8_t padding_bits,
+                                const hb_tree *tree, uint8_t *out, size_t out_cap, size_t *out_n);
+
 /* ---------------------------------------------------------------- device-buffer API (ctx stream) */
 /* d_hist256: 256 x u64 on the device; overwritten.  No host sync. */
 hb_status hb_histogram_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, uint64_t *d_hist256);

@@ -1,10 +1,10 @@
 """Multi-GPU path: contiguous input shards, one process per GPU, torch.distributed for the two tiny exchanges.
 
 compress:
-    local histogram kernel -> all_reduce(SUM) of the 256 bins (2 KiB) -> every rank builds the identical tree on the
-    host -> local bit total = sum(local_hist * len) -> all_gather of the G totals (8 B each) -> exclusive scan =
-    the shard's GLOBAL bit offset -> encode kernel with start_bit = offset % 8 into a buffer whose byte 0 is global
-    byte offset // 8.  Concatenating the shard buffers (OR-ing the one byte two neighbours may share) gives exactly
+    local histogram kernel -> ONE all_gather of the G local 256-bin histograms (G x 2 KiB): their sum is the
+    all-reduced global histogram, from which every rank builds the identical tree on the host, and
+    sum(hist_g * len) for every g gives all shard bit totals at once -> exclusive scan = the shard's GLOBAL bit
+    offset -> encode kernel with start_bit = offset % 8 into a buffer whose byte 0 is global byte offset // 8.  Concatenating the shard buffers (OR-ing the one byte two neighbours may share) gives exactly
     the single-GPU stream; `gather_stream` does that and the tests check it against the oracle.
 decompress:
     (a) of shards produced by `compress`: every rank knows its first code-word start exactly (start_bit), no exchange.
@@ -26,10 +26,6 @@ class ShardedCodec:
     def __init__(self, engine, world: int = 1, rank: int = 0, dist=None):
         self.eng, self.world, self.rank, self.dist = engine, world, rank, dist
         self.last_info = None
-        dev = engine.device
-        self._hist2 = torch.zeros(2, 256, dtype=torch.int64, device=dev)
-        self._bits = torch.zeros(max(world, 1), dtype=torch.int64, device=dev)
-        self._mine = torch.zeros(1, dtype=torch.int64, device=dev)
 
     # ------------------------------------------------------------ helpers
     def _event(self):
@@ -45,22 +41,20 @@ class ShardedCodec:
         local = eng.histogram(data)
         if marks is not None:
             marks["hist"] = (a, self._event())
-        self._hist2[0].copy_(local)
-        self._hist2[1].copy_(local)
         if self.world > 1:
-            dist.all_reduce(self._hist2[1], op=dist.ReduceOp.SUM)
-        h = self._hist2.cpu().numpy()                       # host sync: the tree needs the global histogram
-        local_w, global_w = h[0].astype(np.uint64), h[1].astype(np.uint64)
+            # ONE exchange: all-gather the G local histograms (G x 2 KiB).  Every rank sums them into the global
+            # histogram (= the all-reduce) and, once the tree is known, also knows every shard's bit total
+            # (= the all-gather of totals + exclusive scan) without a second collective.
+            parts = [torch.zeros_like(local) for _ in range(self.world)]
+            dist.all_gather(parts, local)
+            h = torch.stack(parts).cpu().numpy().astype(np.uint64)      # host sync: the tree needs the histogram
+        else:
+            h = local.cpu().numpy().astype(np.uint64)[None, :]
+        global_w = h.sum(axis=0)
         tree = eng.tree_from_weights(global_w)
         lens = np.array([tree.raw.code_len[b] for b in range(256)], dtype=np.uint64)
-        my_bits = int((local_w * lens).sum())
-        if self.world > 1:
-            self._mine[0] = my_bits
-            parts = [torch.zeros_like(self._mine) for _ in range(self.world)]
-            dist.all_gather(parts, self._mine)
-            all_bits = [int(x.item()) for x in parts]
-        else:
-            all_bits = [my_bits]
+        all_bits = [int(x) for x in (h * lens[None, :]).sum(axis=1)]
+        my_bits = all_bits[self.rank]
         offset = sum(all_bits[: self.rank])
         total = sum(all_bits)
         start_bit = offset % 8

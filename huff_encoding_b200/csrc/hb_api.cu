@@ -293,7 +293,7 @@ void build_dec_tables(const hb_tree *tree, hb::DecTables *t) {
     for (uint32_t p = 0; p < (1u << K); p++) {
         if (leaf(root)) {
             // comp.rs:496,506-509: a lone root emits its letter for every bit
-            t->lut[p] = static_cast<uint16_t>(tree->nodes[root].letter | (1u << 8));
+            t->lut[p] = static_cast<uint16_t>(1u | (static_cast<uint32_t>(tree->nodes[root].letter) << 8));
             t->cnt[p] = static_cast<uint8_t>((K << 4) | K);
             continue;
         }
@@ -305,8 +305,9 @@ void build_dec_tables(const hb_tree *tree, hb::DecTables *t) {
             node = bit ? tree->nodes[node].right : tree->nodes[node].left;
             used++;
         }
-        t->lut[p] = leaf(node) ? static_cast<uint16_t>(tree->nodes[node].letter | (used << 8))
-                               : static_cast<uint16_t>(0x8000u | node);
+        // short code: len | letter << 8 ; long code: bit 7, node index in bits 8-15 (low) and 4-6 (high), len field 0
+        t->lut[p] = leaf(node) ? static_cast<uint16_t>(static_cast<uint32_t>(used) | (static_cast<uint32_t>(tree->nodes[node].letter) << 8))
+                               : static_cast<uint16_t>(0x80u | ((node & 0xFFu) << 8) | (((node >> 8) & 7u) << 4));
         // greedy run of complete code words inside the K bits
         int pos = 0, letters = 0;
         for (;;) {

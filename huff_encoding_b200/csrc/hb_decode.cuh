@@ -48,12 +48,14 @@ constexpr uint32_t kWinBits = kWinWords * 32u;
 constexpr int kLutBits = 12;
 constexpr uint32_t kEnd32 = 0xFFFFFFFFu;
 constexpr uint64_t kEnd64 = ~0ull;
-constexpr int kLookbackBits = 512;                             // in-CTA look-back window W (thread 0 uses the full halo)
+constexpr int kLookbackBits = 192;                             // in-CTA look-back window W (thread 0 uses the full halo);
+                                                               // measured resynchronisation distance: mean 16, p99 < 90 bits
 constexpr int kScanGroup = 1024;                               // CTAs per offset-scan group
 constexpr int kGroup = 32;                                     // letters per 256-bit store in the write pass
 
 struct DecTables {                     // device resident, built on the host from the hb_tree
-    uint16_t lut[1 << kLutBits];       // bit15 = 0: letter | len << 8 ; bit15 = 1: node index to continue from
+    uint16_t lut[1 << kLutBits];       // bit7 = 0: len (bits 0-3) | letter << 8 ; bit7 = 1: long code, continue at node
+                                       // ((e >> 8) | ((e >> 4) & 7) << 8); its len field is 0
     uint8_t  cnt[1 << kLutBits];       // (bits consumed << 4) | letters completed, 0 if the first code is longer than 12
     uint32_t nodes[HB_MAX_NODES];      // left | right << 16 ; leaf: left = 0xFFFF, right = letter
     uint32_t root;
@@ -100,35 +102,34 @@ __device__ __forceinline__ uint32_t win_bit(uint32_t win, uint32_t q) {
 }
 
 // ---------------------------------------------------------------- register bit window
+// Two consecutive stream words and a bit offset: peek = one funnel shift, consume = one add, and a predicated
+// one-word refill whenever the offset crosses 32.
 struct BitReader {
-    uint32_t hi, lo;        // next `have` bits of the stream, MSB first, in hi:lo
-    uint32_t have, wi, q;   // valid bits, next word to load, stream position of the MSB of hi
+    uint32_t w0, w1;        // stream words wi-2 and wi-1 (MSB first)
+    uint32_t s, wi, q;      // bit offset inside w0 (< 32), next word to load, stream position (= 32*(wi-2) + s)
     __device__ __forceinline__ void init(uint32_t win, uint32_t q0) {
-        q = q0; wi = q0 >> 5;
-        const uint32_t s = q0 & 31;
-        const uint32_t w0 = lds32(win_word_addr(win, wi)), w1 = lds32(win_word_addr(win, wi + 1));
-        hi = __funnelshift_l(w1, w0, s);
-        lo = w1 << s;
-        have = 64 - s;
+        q = q0; wi = q0 >> 5; s = q0 & 31;
+        w0 = lds32(win_word_addr(win, wi));
+        w1 = lds32(win_word_addr(win, wi + 1));
         wi += 2;
     }
-    __device__ __forceinline__ void refill(uint32_t win) {          // afterwards have >= 33
-        if (have <= 32) {                                            // all valid bits are in hi, lo == 0
-            const uint32_t w = lds32(win_word_addr(win, wi));
-            hi |= __funnelshift_rc(w, 0u, have);
-            lo = __funnelshift_rc(0u, w, have);
-            have += 32;
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(w1, w0, s) >> (32 - kLutBits); }
+    __device__ __forceinline__ void skip(uint32_t win, uint32_t l) {  // l < 32
+        s += l;
+        q += l;
+        if (s >= 32) {
+            s -= 32;
+            w0 = w1;
+            w1 = lds32(win_word_addr(win, wi));
             wi++;
         }
     }
-    __device__ __forceinline__ uint32_t peek() const { return hi >> (32 - kLutBits); }
-    __device__ __forceinline__ void skip(uint32_t l) {               // l < 32
-        hi = __funnelshift_l(lo, hi, l);
-        lo <<= l;
-        have -= l;
-        q += l;
-    }
 };
+
+__device__ __forceinline__ uint32_t lut_is_long(uint32_t e) { return e & 0x80u; }
+__device__ __forceinline__ uint32_t lut_len(uint32_t e) { return e & 0xFu; }
+__device__ __forceinline__ uint32_t lut_letter(uint32_t e) { return e >> 8; }
+__device__ __forceinline__ uint32_t lut_node(uint32_t e) { return (e >> 8) | (((e >> 4) & 7u) << 8); }
 
 // Decode one code word starting at window bit q (table + tree walk, any length).  Returns its length, 0 if it would
 // end after q_avail.
@@ -137,11 +138,11 @@ __device__ __noinline__ uint32_t dec_one_slow(DecShared s, uint32_t q, uint32_t 
     const uint32_t x = __funnelshift_l(lds32(win_word_addr(s.win, i + 1)), lds32(win_word_addr(s.win, i)), q & 31);
     const uint32_t e = lds16(s.lut + ((x >> (32 - kLutBits)) << 1));
     uint32_t len;
-    if (!(e & 0x8000u)) {
-        len = (e >> 8) & 0xFu;
-        letter = e & 0xFFu;
+    if (!lut_is_long(e)) {
+        len = lut_len(e);
+        letter = lut_letter(e);
     } else {
-        uint32_t node = e & 0x3FFu;
+        uint32_t node = lut_node(e);
         len = kLutBits;
         for (;;) {
             const uint32_t nd = lds32(s.nodes + (node << 2));
@@ -159,18 +160,17 @@ __device__ __noinline__ uint32_t dec_one_slow(DecShared s, uint32_t q, uint32_t 
 __device__ __forceinline__ uint32_t dec_run(DecShared s, uint32_t q, uint32_t q_stop, uint32_t q_avail, uint32_t &count) {
     uint32_t n = 0;
     if (q == kEnd32) { count = 0; return kEnd32; }
-    const uint32_t fast_stop = min(q_stop, q_avail);
-    if (q + kLutBits <= fast_stop) {
-        const uint32_t last = fast_stop - kLutBits;                  // multi-letter steps while q <= last
+    if (q < q_stop && q_stop + 2 * kLutBits <= q_avail) {
+        // common case (everything but the very end of the stream): no code word can run past q_avail here
         BitReader rd;
         rd.init(s.win, q);
-        while (rd.q <= last) {
-            rd.refill(s.win);
+        const uint32_t last = q_stop >= kLutBits ? q_stop - kLutBits : 0;
+        while (rd.q <= last && rd.q + kLutBits <= q_stop) {              // multi-letter steps: all inside [q, q_stop)
             const uint32_t c = lds8(s.cnt + rd.peek());
             if (c) {
-                rd.skip(c >> 4);
+                rd.skip(s.win, c >> 4);
                 n += c & 15u;
-            } else {                                                 // first code longer than 12 bits
+            } else {                                                     // first code longer than 12 bits
                 uint32_t letter;
                 const uint32_t len = dec_one_slow(s, rd.q, q_avail, letter);
                 if (!len) { count = n; return kEnd32; }
@@ -178,9 +178,23 @@ __device__ __forceinline__ uint32_t dec_run(DecShared s, uint32_t q, uint32_t q_
                 rd.init(s.win, rd.q + len);
             }
         }
-        q = rd.q;
+        while (rd.q < q_stop) {                                          // last few letters: one per lookup
+            const uint32_t e = lds16(s.lut + (rd.peek() << 1));
+            if (!lut_is_long(e)) {
+                rd.skip(s.win, lut_len(e));
+                n++;
+            } else {
+                uint32_t letter;
+                const uint32_t len = dec_one_slow(s, rd.q, q_avail, letter);
+                if (!len) { count = n; return kEnd32; }
+                n++;
+                rd.init(s.win, rd.q + len);
+            }
+        }
+        count = n;
+        return rd.q;
     }
-    while (q < q_stop) {
+    while (q < q_stop) {                                                 // end of the stream: every step checked
         uint32_t letter;
         const uint32_t len = dec_one_slow(s, q, q_avail, letter);
         if (!len) { count = n; return kEnd32; }
@@ -566,10 +580,9 @@ dec_write_kernel(DecParams p, const DecTables *__restrict__ tables, const uint32
         if (pos < lo && src.rd.q < q_safe_group) {                            // letters my predecessor writes (< 32)
             BitReader rd = src.rd;
             while (pos < lo) {
-                rd.refill(c.sh.win);
                 const uint32_t e = lds16(c.sh.lut + (rd.peek() << 1));
-                if (e & 0x8000u) break;
-                rd.skip((e >> 8) & 0xFu);
+                if (lut_is_long(e)) break;
+                rd.skip(c.sh.win, lut_len(e));
                 pos++;
             }
             src.rd = rd;
@@ -587,16 +600,16 @@ dec_write_kernel(DecParams p, const DecTables *__restrict__ tables, const uint32
                 uint32_t escape = 0;
 #pragma unroll
                 for (int j = 0; j < kGroup; j++) {
-                    rd.refill(c.sh.win);
                     const uint32_t e = lds16(c.sh.lut + (rd.peek() << 1));
                     escape |= e;
-                    rd.skip((e >> 8) & 0xFu);
-                    if ((j & 3) == 0) v[j >> 2] = e & 0xFFu;
-                    else if ((j & 3) == 1) v[j >> 2] = __byte_perm(v[j >> 2], e, 0x3240);
-                    else if ((j & 3) == 2) v[j >> 2] = __byte_perm(v[j >> 2], e, 0x3410);
-                    else v[j >> 2] = __byte_perm(v[j >> 2], e, 0x4210);
+                    rd.skip(c.sh.win, lut_len(e));
+                    // the letter sits in byte 1 of e: one PRMT drops it into byte j%4 of the output word
+                    if ((j & 3) == 0) v[j >> 2] = __byte_perm(e, 0u, 0x4441);
+                    else if ((j & 3) == 1) v[j >> 2] = __byte_perm(v[j >> 2], e, 0x3250);
+                    else if ((j & 3) == 2) v[j >> 2] = __byte_perm(v[j >> 2], e, 0x3510);
+                    else v[j >> 2] = __byte_perm(v[j >> 2], e, 0x5210);
                 }
-                if (!(escape & 0x8000u)) {
+                if (!lut_is_long(escape)) {
                     stg256(out + pos, v);
                     src.rd = rd;
                     done = true;

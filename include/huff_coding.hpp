@@ -148,7 +148,8 @@ inline CompressData compress(const std::vector<uint8_t> &letters) {
 inline CompressData compress_with_tree(const std::vector<uint8_t> &letters, HuffTree tree) {
     uint8_t *p = nullptr, pad = 0, missing = 0;
     size_t n = 0;
-    detail::check(hb_compress_with_tree_u8(detail::ctx(), letters.data(), letters.size(), tree.raw(), &p, &n, &pad, &missing), missing);
+    const hb_status st = hb_compress_with_tree_u8(detail::ctx(), letters.data(), letters.size(), tree.raw(), &p, &n, &pad, &missing);
+    detail::check(st, missing);                              // (two statements: `missing` must be read after the call)
     std::vector<uint8_t> v(p, p + n);
     hb_free(p);
     return CompressData(std::move(v), pad, std::move(tree));

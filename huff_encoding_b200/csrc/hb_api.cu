@@ -107,6 +107,7 @@ struct hb_ctx {
     DecResult *h_dec_result = nullptr;   // pinned
     uint32_t *d_n_dirty = nullptr;
     int dec_count_grid = 0, dec_write_grid = 0;
+    int cnt_bits = 13;                   // HB_CNT_BITS=12|13|14: index width of the multi-letter count table (13 measured best)
     hb::DecParams last_dec;
     uint64_t last_dec_total = 0;
     bool last_dec_valid = false;
@@ -279,7 +280,7 @@ hb_status check_encodable(const uint64_t weights[256], const hb_tree *tree, uint
 }
 
 // ---------------------------------------------------------------- decoder
-void build_dec_tables(const hb_tree *tree, hb::DecTables *t) {
+void build_dec_tables(const hb_tree *tree, hb::DecTables *t, int cnt_bits) {
     std::memset(t, 0, sizeof *t);
     auto leaf = [&](uint32_t n) { return tree->nodes[n].left == HB_NO_CHILD; };
     for (uint32_t i = 0; i < tree->n_nodes && i < HB_MAX_NODES; i++) {
@@ -294,7 +295,6 @@ void build_dec_tables(const hb_tree *tree, hb::DecTables *t) {
         if (leaf(root)) {
             // comp.rs:496,506-509: a lone root emits its letter for every bit
             t->lut[p] = static_cast<uint16_t>(1u | (static_cast<uint32_t>(tree->nodes[root].letter) << 8));
-            t->cnt[p] = static_cast<uint8_t>((K << 4) | K);
             continue;
         }
         // first code word
@@ -308,20 +308,24 @@ void build_dec_tables(const hb_tree *tree, hb::DecTables *t) {
         // short code: len | letter << 8 ; long code: bit 7, node index in bits 8-15 (low) and 4-6 (high), len field 0
         t->lut[p] = leaf(node) ? static_cast<uint16_t>(static_cast<uint32_t>(used) | (static_cast<uint32_t>(tree->nodes[node].letter) << 8))
                                : static_cast<uint16_t>(0x80u | ((node & 0xFFu) << 8) | (((node >> 8) & 7u) << 4));
-        // greedy run of complete code words inside the K bits
+    }
+    // multi-letter count table over CB bits: greedy run of complete code words
+    const int CB = cnt_bits;
+    for (uint32_t p = 0; p < (1u << CB); p++) {
+        if (leaf(root)) { t->cnt[p] = static_cast<uint8_t>((CB << 4) | CB); continue; }
         int pos = 0, letters = 0;
         for (;;) {
             uint32_t nd = root;
             int q = pos;
-            while (q < K && !leaf(nd)) {
-                const int bit = (p >> (K - 1 - q)) & 1;
+            while (q < CB && !leaf(nd)) {
+                const int bit = (p >> (CB - 1 - q)) & 1;
                 nd = bit ? tree->nodes[nd].right : tree->nodes[nd].left;
                 q++;
             }
             if (!leaf(nd)) break;
             pos = q;
             letters++;
-            if (pos >= K) break;
+            if (pos >= CB) break;
         }
         t->cnt[p] = static_cast<uint8_t>((pos << 4) | letters);
     }
@@ -330,7 +334,7 @@ void build_dec_tables(const hb_tree *tree, hb::DecTables *t) {
 hb_status upload_dec_tables(hb_ctx *ctx, const hb_tree *tree) {
     if (ctx->dec_tree_valid && same_nodes(ctx->dec_tree_cached, *tree)) return HB_OK;
     static thread_local hb::DecTables t;
-    build_dec_tables(tree, &t);
+    build_dec_tables(tree, &t, ctx->cnt_bits);
     HB_CUDA(cudaMemcpyAsync(ctx->d_dec_tables, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream));
     HB_CUDA(cudaStreamSynchronize(ctx->stream));       // `t` is reused by the next call
     ctx->dec_tree_cached = *tree;
@@ -415,6 +419,7 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
     p.len_gcd = tree->len_gcd ? tree->len_gcd : 1;
     p.fixed_len = (tree->min_len == tree->max_len) ? tree->max_len : 0;
     p.max_len = tree->max_len ? tree->max_len : 1;
+    p.cnt_bits = static_cast<uint32_t>(ctx->cnt_bits);
     if (tree->nodes[tree->root].left == HB_NO_CHILD) { p.fixed_len = 1; p.len_gcd = 1; }
     p.first_block = static_cast<uint32_t>(first_block);
     p.n_blocks = static_cast<uint32_t>(n_blocks);
@@ -424,7 +429,10 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
     p.blk_count = ctx->blk_count.p;
 
     const int grid = static_cast<int>(std::min<uint64_t>(ctx->dec_count_grid, n_blocks));
-    hb::dec_count_kernel<<<grid, hb::kDecThreads, hb::kDecSmemCount, ctx->stream>>>(p, ctx->d_dec_tables);
+    const size_t smem_count = hb::dec_smem_count(ctx->cnt_bits);
+    if (ctx->cnt_bits == 14) hb::dec_count_kernel<14><<<grid, hb::kDecThreads, smem_count, ctx->stream>>>(p, ctx->d_dec_tables);
+    else if (ctx->cnt_bits == 13) hb::dec_count_kernel<13><<<grid, hb::kDecThreads, smem_count, ctx->stream>>>(p, ctx->d_dec_tables);
+    else hb::dec_count_kernel<12><<<grid, hb::kDecThreads, smem_count, ctx->stream>>>(p, ctx->d_dec_tables);
     ctx->launches++;
     HB_CUDA(cudaGetLastError());
 
@@ -442,7 +450,9 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
         if (ctx->h_dec_result->n_dirty == 0) break;
         if (round == 1) { g_last_error = "decoder chain repair did not converge"; return HB_ERR_CUDA; }
         // rare: a chunk whose speculative entry was wrong even after a 1024-bit look-back -> serial repair
-        hb::dec_fix_kernel<<<1, hb::kDecThreads, hb::kDecSmemCount, ctx->stream>>>(p, ctx->d_dec_tables, ctx->dirty.p);
+        if (ctx->cnt_bits == 14) hb::dec_fix_kernel<14><<<1, hb::kDecThreads, smem_count, ctx->stream>>>(p, ctx->d_dec_tables, ctx->dirty.p);
+        else if (ctx->cnt_bits == 13) hb::dec_fix_kernel<13><<<1, hb::kDecThreads, smem_count, ctx->stream>>>(p, ctx->d_dec_tables, ctx->dirty.p);
+        else hb::dec_fix_kernel<12><<<1, hb::kDecThreads, smem_count, ctx->stream>>>(p, ctx->d_dec_tables, ctx->dirty.p);
         ctx->launches++;
         HB_CUDA(cudaGetLastError());
     }
@@ -548,8 +558,13 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
         HB_CUDA(cudaMallocHost(&ctx->h_dec_result, sizeof(DecResult)));
         HB_CUDA(cudaMallocHost(&ctx->h_hist, 256 * sizeof(uint64_t)));
         HB_CUDA(cudaMallocHost(&ctx->h_total_bits, sizeof(unsigned long long)));
-        HB_CUDA(cudaFuncSetAttribute(hb::dec_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::kDecSmemCount)));
-        HB_CUDA(cudaFuncSetAttribute(hb::dec_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::kDecSmemCount)));
+        { const char *cb = std::getenv("HB_CNT_BITS"); if (cb) { int v = std::atoi(cb); if (v >= 12 && v <= 14) ctx->cnt_bits = v; } }
+        HB_CUDA(cudaFuncSetAttribute(hb::dec_count_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::dec_smem_count(12))));
+        HB_CUDA(cudaFuncSetAttribute(hb::dec_count_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::dec_smem_count(13))));
+        HB_CUDA(cudaFuncSetAttribute(hb::dec_count_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::dec_smem_count(14))));
+        HB_CUDA(cudaFuncSetAttribute(hb::dec_fix_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::dec_smem_count(12))));
+        HB_CUDA(cudaFuncSetAttribute(hb::dec_fix_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::dec_smem_count(13))));
+        HB_CUDA(cudaFuncSetAttribute(hb::dec_fix_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::dec_smem_count(14))));
         HB_CUDA(cudaFuncSetAttribute(hb::dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::kDecSmemWrite)));
         int occ = 0;
         HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::hist_lane_columns_kernel, hb::kHistThreads, 0));
@@ -560,7 +575,9 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
         HB_CUDA(cudaFuncSetAttribute(hb::encode_regions_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::enc_smem_bytes(4))));
         HB_CUDA(cudaFuncSetAttribute(hb::encode_regions_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::enc_smem_bytes(2))));
         HB_CUDA(cudaFuncSetAttribute(hb::encode_regions_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::enc_smem_bytes(1))));
-        HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::dec_count_kernel, hb::kDecThreads, hb::kDecSmemCount));
+        if (ctx->cnt_bits == 14) HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::dec_count_kernel<14>, hb::kDecThreads, hb::dec_smem_count(14)));
+        else if (ctx->cnt_bits == 13) HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::dec_count_kernel<13>, hb::kDecThreads, hb::dec_smem_count(13)));
+        else HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::dec_count_kernel<12>, hb::kDecThreads, hb::dec_smem_count(12)));
         ctx->dec_count_grid = ctx->sm_count * std::max(occ, 1);
         HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::dec_write_kernel, hb::kDecThreads, hb::kDecSmemWrite));
         ctx->dec_write_grid = ctx->sm_count * std::max(occ, 1);

@@ -46,6 +46,7 @@ constexpr int kWinWords = kHaloWords + kChunkWords + kHaloWords;
 constexpr int kWinPhys = kWinWords + (kWinWords >> 5) + 4;     // padded: phys(i) = i + i/32 (+ slack for look-ahead)
 constexpr uint32_t kWinBits = kWinWords * 32u;
 constexpr int kLutBits = 12;
+constexpr int kCntBitsMax = 14;                                 // the multi-letter count table may look at up to 14 bits
 constexpr uint32_t kEnd32 = 0xFFFFFFFFu;
 constexpr uint64_t kEnd64 = ~0ull;
 constexpr int kLookbackBits = 192;                             // in-CTA look-back window W (thread 0 uses the full halo);
@@ -56,7 +57,8 @@ constexpr int kGroup = 32;                                     // letters per 25
 struct DecTables {                     // device resident, built on the host from the hb_tree
     uint16_t lut[1 << kLutBits];       // bit7 = 0: len (bits 0-3) | letter << 8 ; bit7 = 1: long code, continue at node
                                        // ((e >> 8) | ((e >> 4) & 7) << 8); its len field is 0
-    uint8_t  cnt[1 << kLutBits];       // (bits consumed << 4) | letters completed, 0 if the first code is longer than 12
+    uint8_t  cnt[1 << kCntBitsMax];    // indexed by the next cnt_bits bits: (bits consumed << 4) | letters completed,
+                                       // 0 if not even one code fits
     uint32_t nodes[HB_MAX_NODES];      // left | right << 16 ; leaf: left = 0xFFFF, right = letter
     uint32_t root;
 };
@@ -70,6 +72,7 @@ struct DecParams {
     uint64_t stream_bit0;              // stream bit index of buffer bit 0 (phase of the gcd alignment)
     uint32_t len_gcd, fixed_len;       // gcd of code lengths; fixed_len != 0 when all codes have that length
     uint32_t max_len;                  // longest code (bounds how far a thread may read past its subsequence)
+    uint32_t cnt_bits;                 // index width of DecTables::cnt in use (12..14)
     uint32_t first_block, n_blocks;    // CTAs cover chunks first_block .. first_block + n_blocks - 1
     uint32_t *sub_info;                // per subsequence (relative to first_block): entry_rel << 16 | count
     uint64_t *blk_entry, *blk_exit;    // per CTA, absolute buffer bits (kEnd64 = none)
@@ -114,6 +117,7 @@ struct BitReader {
         wi += 2;
     }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(w1, w0, s) >> (32 - kLutBits); }
+    __device__ __forceinline__ uint32_t peek_bits(uint32_t k) const { return __funnelshift_l(w1, w0, s) >> (32 - k); }
     __device__ __forceinline__ void skip(uint32_t win, uint32_t l) {  // l < 32
         s += l;
         q += l;
@@ -157,20 +161,20 @@ __device__ __noinline__ uint32_t dec_one_slow(DecShared s, uint32_t q, uint32_t 
 
 // Advance from q over whole code words while q < q_stop; count them.  Returns the first code-word start >= q_stop,
 // or kEnd32 when a code word does not fit below q_avail.
+template <int CB>
 __device__ __forceinline__ uint32_t dec_run(DecShared s, uint32_t q, uint32_t q_stop, uint32_t q_avail, uint32_t &count) {
     uint32_t n = 0;
     if (q == kEnd32) { count = 0; return kEnd32; }
-    if (q < q_stop && q_stop + 2 * kLutBits <= q_avail) {
+    if (q < q_stop && q_stop + 2 * CB <= q_avail) {
         // common case (everything but the very end of the stream): no code word can run past q_avail here
         BitReader rd;
         rd.init(s.win, q);
-        const uint32_t last = q_stop >= kLutBits ? q_stop - kLutBits : 0;
-        while (rd.q <= last && rd.q + kLutBits <= q_stop) {              // multi-letter steps: all inside [q, q_stop)
-            const uint32_t c = lds8(s.cnt + rd.peek());
+        while (rd.q + CB <= q_stop) {                                    // multi-letter steps: all inside [q, q_stop)
+            const uint32_t c = lds8(s.cnt + rd.peek_bits(CB));
             if (c) {
                 rd.skip(s.win, c >> 4);
                 n += c & 15u;
-            } else {                                                     // first code longer than 12 bits
+            } else {                                                     // first code longer than CB bits
                 uint32_t letter;
                 const uint32_t len = dec_one_slow(s, rd.q, q_avail, letter);
                 if (!len) { count = n; return kEnd32; }
@@ -206,14 +210,14 @@ __device__ __forceinline__ uint32_t dec_run(DecShared s, uint32_t q, uint32_t q_
 }
 
 __device__ __forceinline__ void dec_load_tables(const DecTables *__restrict__ t, uint16_t *s_lut, uint8_t *s_cnt,
-                                                uint32_t *s_nodes) {
+                                                uint32_t *s_nodes, int cnt_bits = kLutBits) {
     const uint32_t *src_lut = reinterpret_cast<const uint32_t *>(t->lut);
     uint32_t *dst_lut = reinterpret_cast<uint32_t *>(s_lut);
     for (int i = threadIdx.x; i < (1 << kLutBits) / 2; i += blockDim.x) dst_lut[i] = src_lut[i];
     if (s_cnt) {
         const uint32_t *src_cnt = reinterpret_cast<const uint32_t *>(t->cnt);
         uint32_t *dst_cnt = reinterpret_cast<uint32_t *>(s_cnt);
-        for (int i = threadIdx.x; i < (1 << kLutBits) / 4; i += blockDim.x) dst_cnt[i] = src_cnt[i];
+        for (int i = threadIdx.x; i < (1 << cnt_bits) / 4; i += blockDim.x) dst_cnt[i] = src_cnt[i];
     }
     for (int i = threadIdx.x; i < HB_MAX_NODES; i += blockDim.x) s_nodes[i] = t->nodes[i];
 }
@@ -264,6 +268,7 @@ __device__ __forceinline__ void dec_load_window(const DecParams &p, uint32_t chu
 }
 
 // The count pass for one chunk.
+template <int CB>
 __device__ void dec_count_block(const DecParams &p, uint32_t blk, uint64_t entry_override, bool use_override,
                                 uint32_t *win, DecShared s, uint32_t *s_exit, uint32_t *s_red) {
     const int t = threadIdx.x;
@@ -307,7 +312,7 @@ __device__ void dec_count_block(const DecParams &p, uint32_t blk, uint64_t entry
                 if (rem) q0 += p.len_gcd - rem;
             }
             uint32_t dummy;
-            entry = q0 >= q_lo ? q0 : dec_run(s, q0, q_lo, q_avail, dummy);
+            entry = q0 >= q_lo ? q0 : dec_run<CB>(s, q0, q_lo, q_avail, dummy);
         }
     }
 
@@ -316,7 +321,7 @@ __device__ void dec_count_block(const DecParams &p, uint32_t blk, uint64_t entry
     bool redo = active;
     for (int round = 0;; round++) {
         if (round > kDecThreads + 1) asm volatile("trap;");   // cannot happen: thread t is final after t rounds
-        if (redo) exitq = dec_run(s, entry, q_hi, q_avail, count);
+        if (redo) exitq = dec_run<CB>(s, entry, q_hi, q_avail, count);
         s_exit[t] = exitq;
         __syncthreads();
         redo = false;
@@ -357,10 +362,10 @@ constexpr size_t dec_align16(size_t x) { return (x + 15) & ~static_cast<size_t>(
 constexpr size_t kDecOffLut = dec_align16(kWinPhys * 4);
 constexpr size_t kDecOffNodes = kDecOffLut + (1 << kLutBits) * 2;
 constexpr size_t kDecOffRed = kDecOffNodes + dec_align16(HB_MAX_NODES * 4);
-constexpr size_t kDecOffCnt = kDecOffRed + 64;
-constexpr size_t kDecOffExit = kDecOffCnt + (1 << kLutBits);
-constexpr size_t kDecSmemCount = kDecOffExit + kDecThreads * 4;
-constexpr size_t kDecSmemWrite = kDecOffCnt;                           // window + lut + nodes + red
+constexpr size_t kDecOffExit = kDecOffRed + 64;
+constexpr size_t kDecOffCnt = kDecOffExit + kDecThreads * 4;
+constexpr size_t dec_smem_count(int cnt_bits) { return kDecOffCnt + (static_cast<size_t>(1) << cnt_bits); }
+constexpr size_t kDecSmemWrite = kDecOffExit;                           // window + lut + nodes + red
 
 struct DecCarve {
     uint32_t *win; uint16_t *lut; uint8_t *cnt; uint32_t *nodes; uint32_t *exit; uint32_t *red;
@@ -381,12 +386,13 @@ __device__ __forceinline__ DecCarve dec_carve(uint8_t *base) {
     return c;
 }
 
+template <int CB>
 __global__ void __launch_bounds__(kDecThreads)
 dec_count_kernel(DecParams p, const DecTables *__restrict__ tables) {
     DecCarve c = dec_carve(dec_smem);
-    dec_load_tables(tables, c.lut, c.cnt, c.nodes);
+    dec_load_tables(tables, c.lut, c.cnt, c.nodes, CB);
     for (uint32_t blk = blockIdx.x; blk < p.n_blocks; blk += gridDim.x)
-        dec_count_block(p, blk, 0, false, c.win, c.sh, c.exit, c.red);
+        dec_count_block<CB>(p, blk, 0, false, c.win, c.sh, c.exit, c.red);
 }
 
 // dirty[j] = 1 when CTA j's entry is not its predecessor's exit.  n_dirty accumulates.
@@ -400,11 +406,12 @@ __global__ void dec_verify_kernel(DecParams p, uint32_t *dirty, uint32_t *n_dirt
 }
 
 // Serial repair of mismatching CTAs (single CTA).  Each repaired chunk may change its exit and dirty its successor.
+template <int CB>
 __global__ void __launch_bounds__(kDecThreads)
 dec_fix_kernel(DecParams p, const DecTables *__restrict__ tables, uint32_t *dirty) {
     DecCarve c = dec_carve(dec_smem);
     __shared__ uint32_t s_next;
-    dec_load_tables(tables, c.lut, c.cnt, c.nodes);
+    dec_load_tables(tables, c.lut, c.cnt, c.nodes, CB);
     uint32_t cur = 1;
     for (;;) {
         // find the next dirty chunk at or after cur
@@ -427,7 +434,7 @@ dec_fix_kernel(DecParams p, const DecTables *__restrict__ tables, uint32_t *dirt
         const uint64_t old_exit = vexit[j];
         const uint64_t entry = vexit[j - 1];
         __syncthreads();
-        dec_count_block(p, j, entry, true, c.win, c.sh, c.exit, c.red);
+        dec_count_block<CB>(p, j, entry, true, c.win, c.sh, c.exit, c.red);
         if (threadIdx.x == 0) {
             dirty[j] = 0;
             if (j + 1 < p.n_blocks && vexit[j] != old_exit) dirty[j + 1] = 1;
@@ -602,13 +609,21 @@ dec_write_kernel(DecParams p, const DecTables *__restrict__ tables, const uint32
                 for (int j = 0; j < kGroup; j++) {
                     const uint32_t e = lds16(c.sh.lut + (rd.peek() << 1));
                     escape |= e;
-                    rd.skip(c.sh.win, lut_len(e));
+                    // consume (the stream position rd.q is recomputed after the group)
+                    rd.s += lut_len(e);
+                    if (rd.s >= 32) {
+                        rd.s -= 32;
+                        rd.w0 = rd.w1;
+                        rd.w1 = lds32(win_word_addr(c.sh.win, rd.wi));
+                        rd.wi++;
+                    }
                     // the letter sits in byte 1 of e: one PRMT drops it into byte j%4 of the output word
                     if ((j & 3) == 0) v[j >> 2] = __byte_perm(e, 0u, 0x4441);
                     else if ((j & 3) == 1) v[j >> 2] = __byte_perm(v[j >> 2], e, 0x3250);
                     else if ((j & 3) == 2) v[j >> 2] = __byte_perm(v[j >> 2], e, 0x3510);
                     else v[j >> 2] = __byte_perm(v[j >> 2], e, 0x5210);
                 }
+                rd.q = ((rd.wi - 2) << 5) + rd.s;
                 if (!lut_is_long(escape)) {
                     stg256(out + pos, v);
                     src.rd = rd;

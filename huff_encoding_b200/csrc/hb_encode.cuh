@@ -14,8 +14,8 @@
 //     so the 32 lookups of a warp never conflict whatever the data;
 //   * a warp scan of the chunk lengths (two rounds packed per 32-bit scan) gives every chunk its bit offset inside the
 //     tile; chunks are OR-ed into a per-warp shared-memory staging stream (<= 3 shared atomics per chunk);
-//   * the staging stream is tile-local; on the way out it is funnel-shifted by (global offset % 32) and stored as
-//     coalesced big-endian 32-bit words.  The word two tiles share is written once, by the later tile, which
+//   * the staging stream is laid out at (global offset % 32), so its words ARE the global stream words and go out as
+//     coalesced big-endian 32-bit stores.  The word two tiles share is written once, by the later tile, which
 //     re-derives the last 32 bits of its predecessor from the predecessor's last 32 letters (every code has >= 1
 //     bit): no pre-zeroed output, no global atomics, no second pass over the input.
 //
@@ -91,7 +91,7 @@ encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable
     // global bit offset of this region: everything the regions before it emit (+ the caller's start bit)
     unsigned long long running = start_bit + enc_region_base(region_hist, blockIdx.x, s_tab, s_red);
 
-    uint32_t *stage = s_stage_all + warp * kEncStageWords;      // [0] = predecessor tail, [1 + m] = local word m
+    uint32_t *stage = s_stage_all + warp * kEncStageWords;      // word m = global stream word (tile offset / 32) + m
     const uint2 *my_tab = s_tab + lane;
     const uint32_t n_rounds = static_cast<uint32_t>((region_end - region_begin + kEncWarps * kTile - 1) / (kEncWarps * kTile));
 
@@ -187,23 +187,6 @@ encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable
         }
         if (!live) continue;
 
-        // ---- OR the chunks into the zeroed staging stream
-        const uint32_t n_local_words = (tile_bits + 31) / 32 + 3;
-        for (uint32_t i = lane; i < n_local_words; i += 32) stage[1 + i] = 0;
-        __syncwarp();
-#pragma unroll
-        for (int r = 0; r < kEncRounds; r++) {
-            const uint32_t L = len[r];
-            if (L == 0) continue;                               // only tail tiles / letters without a code
-            const unsigned long long top = val[r] << (64 - L);  // left-aligned chunk
-            const uint32_t hi = static_cast<uint32_t>(top >> 32), lo = static_cast<uint32_t>(top);
-            const uint32_t w = 1 + (off[r] >> 5), s = off[r] & 31;
-            atomicOr(&stage[w], hi >> s);
-            if (s + L > 32) atomicOr(&stage[w + 1], __funnelshift_r(lo, hi, s));
-            if (s + L > 64) atomicOr(&stage[w + 2], __funnelshift_r(0u, lo, s));
-        }
-        __syncwarp();
-
         // ---- last 32 bits of the predecessor tile, recomputed from its last 32 letters
         uint32_t pred_tail = 0;
         if (tile_base > 0) {
@@ -221,24 +204,39 @@ encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable
             pred_tail = __reduce_or_sync(0xFFFFFFFFu, piece);
         }
 
-        const bool is_last_tile = tile_base + kTile >= n;
-        if (lane == 0) {
-            stage[0] = pred_tail;
-            if (is_last_tile && total_bits_out) *total_bits_out = excl + tile_bits - start_bit;
+        // ---- OR the chunks into the zeroed staging stream, already shifted by (global offset % 32): staging word m
+        //      is global word W0 + m, whose first rr bits are the predecessor's last rr bits
+        const uint32_t rr = static_cast<uint32_t>(excl & 31);
+        const uint32_t n_local_words = (rr + tile_bits + 31) / 32 + 3;
+        for (uint32_t i = lane; i < n_local_words; i += 32) stage[i] = 0;
+        __syncwarp();
+        if (lane == 0 && rr) atomicOr(&stage[0], pred_tail << (32 - rr));   // OR: other lanes' chunks share word 0
+#pragma unroll
+        for (int r = 0; r < kEncRounds; r++) {
+            const uint32_t L = len[r];
+            if (L == 0) continue;                               // only tail tiles / letters without a code
+            const unsigned long long top = val[r] << (64 - L);  // left-aligned chunk
+            const uint32_t hi = static_cast<uint32_t>(top >> 32), lo = static_cast<uint32_t>(top);
+            const uint32_t at = off[r] + rr;
+            const uint32_t w = at >> 5, s = at & 31;
+            atomicOr(&stage[w], hi >> s);
+            if (s + L > 32) atomicOr(&stage[w + 1], __funnelshift_r(lo, hi, s));
+            if (s + L > 64) atomicOr(&stage[w + 2], __funnelshift_r(0u, lo, s));
         }
+        const bool is_last_tile = tile_base + kTile >= n;
+        if (lane == 0 && is_last_tile && total_bits_out) *total_bits_out = excl + tile_bits - start_bit;
         __syncwarp();
 
-        // ---- copy out: global word W0+m = funnel(local[m-1], local[m]) >> r, stored big-endian
-        const uint32_t rr = static_cast<uint32_t>(excl & 31);
+        // ---- copy out: coalesced big-endian 32-bit stores of the whole words; the last partial word stays with the
+        //      next tile, except at the very end of the stream
         const unsigned long long w0 = excl >> 5;
         const unsigned long long end_bit = excl + tile_bits;
         const uint32_t n_full = static_cast<uint32_t>((end_bit >> 5) - w0);
         uint32_t *dst = out32 + w0;
-        for (uint32_t m = lane; m < n_full; m += 32)
-            st_stream_u32(dst + m, bswap32(__funnelshift_r(stage[1 + m], stage[m], rr)));
+        for (uint32_t m = lane; m < n_full; m += 32) st_stream_u32(dst + m, bswap32(stage[m]));
         if (is_last_tile && (end_bit & 31) && lane == 0) {
             // the stream's final partial word: pad bits are zero (comp.rs:446-447), write only the bytes that exist
-            const uint32_t word = __funnelshift_r(stage[1 + n_full], stage[n_full], rr);
+            const uint32_t word = stage[n_full];
             const uint32_t n_bytes = (static_cast<uint32_t>(end_bit & 31) + 7) / 8;
             uint8_t *dst8 = reinterpret_cast<uint8_t *>(dst + n_full);
             for (uint32_t k = 0; k < n_bytes; k++) dst8[k] = static_cast<uint8_t>(word >> (24 - 8 * k));

@@ -352,8 +352,15 @@ def run_ours(args):
         dom = max([k for k in phases if kern[k]["frac"] is not None], key=lambda k: phase_ms[k])
         dec_ms = phase_ms["dec_count"] + phase_ms["dec_write"]
         comp_ms = phase_ms["hist"] + phase_ms["encode"]
+        traffic, traffic_src = None, None
+        try:                                              # measured DRAM bytes per launch from the committed ncu capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+            traffic = tj.get(f"{args.workload}:{n}", {}).get(dom)
+            traffic_src = tj.get("_source") if traffic is not None else None
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": kern[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernels": kern,
                 "compress": {"ms": round(comp_ms, 4), "algorithmic_bytes": 2 * n + c_bytes,
                              "frac": round((2 * n + c_bytes) / (comp_ms * 1e-3) / 1e9 / peak, 4)},

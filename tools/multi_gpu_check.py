@@ -54,6 +54,7 @@ cut = [n_bytes * g // world // 16 * 16 for g in range(world)] + [n_bytes]
 b0 = max(cut[rank] - 4096, 0)
 b1 = min(cut[rank + 1] + 4096, n_bytes)
 buf = pad4[b0: ((b1 + 15) // 16) * 16].contiguous()
+torch.cuda.synchronize()        # buf was produced on the default stream; the engine stream must not race it
 with torch.cuda.stream(eng.stream):
     out, cnt, letter_off = codec.decompress_byte_sharded(buf, b0, cut[rank], cut[rank + 1], total_bits, info["tree"],
                                                          lambda k: torch.zeros(k + 64, dtype=torch.uint8, device=dev))

@@ -343,3 +343,52 @@ def test_config1_one_gib_uniform_properties(eng):
     assert np.array_equal(out[: kb // 8].cpu().numpy(), comp_k[: kb // 8])
     dec, m = eng.decompress(out, clen, pad, tree)
     assert m == n and torch.equal(dec[:m], d)
+
+
+# ---------------------------------------------------------------- SURVEY 8f "next" rows
+def test_n3_foreign_tree_deeper_than_64_bits(hb):
+    # a foreign tree (as try_from_bin may deliver it) whose codes reach 79 bits: the decoder walks any depth; the
+    # encoder refuses letters whose code exceeds 64 bits
+    fib = [1, 1]
+    while len(fib) < 80:
+        fib.append(fib[-1] + fib[-2])
+    pairs = [(b, fib[b]) for b in range(80)]
+    tree = hb.HuffTree.from_weights(pairs)
+    otree = O.tree_from_pairs([p[0] for p in pairs], [p[1] for p in pairs])
+    assert tree.read_codes() == otree.codes() and tree.raw.max_len == 79
+    rng = np.random.default_rng(4)
+    deep = rng.integers(0, 80, size=50_000).astype(np.uint8)             # every depth, long codes everywhere
+    comp, pad = O.compress_with_tree(deep, otree)
+    got = hb.decompress(hb.CompressData(comp, pad, tree))
+    assert np.array_equal(got, deep), _first_diff(got, deep)
+    blob = hb.CompressData(comp, pad, tree).to_bytes()                    # through the container as a foreign file
+    again = hb.CompressData.try_from_bytes(blob)
+    assert np.array_equal(hb.decompress(again), deep)
+    shallow = rng.integers(20, 80, size=200_000).astype(np.uint8)         # codes <= 61 bits: the encoder takes them
+    cd = hb.compress_with_tree(shallow, tree)
+    c2, p2 = O.compress_with_tree(shallow, otree)
+    assert np.array_equal(cd.comp_bytes(), c2) and cd.padding_bits() == p2
+    with pytest.raises(RuntimeError, match="longer than 64"):
+        hb.compress_with_tree(deep, tree)
+
+
+def test_n2_cli_file_round_trip(hb, tmp_path):
+    from huff_encoding_b200 import cli
+    src = tmp_path / "notes.txt"
+    data = np.concatenate([G.english(300_000), np.zeros(1000, np.uint8)])     # has 0x00, no 0xFF: ByteWeights quirk path
+    data.tofile(src)
+    assert cli.main(["-n", str(src), str(tmp_path / "notes.txt")]) == 0       # huff/src/cli.rs: ".hff" is appended
+    hff = tmp_path / "notes.txt.hff"
+    blob = np.fromfile(hff, dtype=np.uint8)
+    # same container a library user gets: header byte, BE u32 tree length, tree, stream (huff/src/comp.rs:47-70)
+    bw = hb.ByteWeights()
+    bw += hb.ByteWeights.threaded_from_bytes(data, 12)
+    tree = hb.HuffTree.from_weights(bw)
+    ref_tree = O.tree_from_pairs([b for b, _ in bw], [w for _, w in bw])
+    assert tree.read_codes() == ref_tree.codes()
+    comp, pad = O.compress_with_tree(data, ref_tree)
+    assert bytes(blob) == bytes(O.to_bytes(comp, pad, ref_tree))
+    out = tmp_path / "back.txt"
+    assert cli.main(["-d", "-n", str(hff), str(out)]) == 0
+    assert np.array_equal(np.fromfile(out, dtype=np.uint8), data)
+    assert cli.parse_block_size("2G") == 2_000_000_000 and cli.parse_block_size("4Ki") == 4096

@@ -139,7 +139,11 @@ hb_status hb_decompress_u8_into(hb_ctx *ctx, const uint8_t *comp, size_t comp_le
 hb_status hb_histogram_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, uint64_t *d_hist256);
 /* Exact stream size for (histogram, tree): sum w[b] * len[b].  Host arithmetic. */
 hb_status hb_stream_bits(const uint64_t weights[256], const hb_tree *tree, uint64_t *bits, uint8_t *missing);
-/* Encoder proper = compress_with_tree's packing loop (comp.rs:422-447).  Writes the stream as if it started at
+/* Encoder proper = compress_with_tree's packing loop (comp.rs:422-447).
+ * The encoder needs the per-region histograms hb_histogram_u8_dev produces as a by-product.  If the immediately
+ * preceding histogram call on this ctx was for the same (d_data, n) they are reused; otherwise the histogram kernel is
+ * run again internally.  Callers that overwrite d_data IN PLACE between hb_histogram_u8_dev and hb_encode_u8_dev must
+ * call hb_histogram_u8_dev again first (the library cannot see device-side writes).  Writes the stream as if it started at
  * bit `start_bit` (0..31) of d_out[0]: the first start_bit bits are left 0 so a neighbouring shard can be OR-ed in
  * (multi-GPU concatenation).  d_out must hold out_cap >= ceil((start_bit + bits)/8) rounded up to 4 bytes.
  * d_total_bits (device u64, optional) receives the number of code bits written.  Letters without a code emit

@@ -166,10 +166,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample = min(args.size, 64 << 20)
+    # bounded sample: calibrate on 4 MiB, then size the per-step sample so that K steps take ~100 s in total
+    rate, _ = cpu_port_round_trip(args.workload, 4 << 20)                     # GB/s
+    budget = int(rate * 1e9 * 100.0 / max(args.steps, 1))
+    sample = max(1 << 20, min(args.size, 64 << 20, budget)) // (1 << 20) * (1 << 20)
     vals = []
     for _ in range(args.warmup):
-        cpu_port_round_trip(args.workload, min(sample, 8 << 20))
+        cpu_port_round_trip(args.workload, min(sample, 2 << 20))
     t_all = 0.0
     for _ in range(args.steps):
         v, dt = cpu_port_round_trip(args.workload, sample)

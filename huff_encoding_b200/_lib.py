@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libhuffb200.so")
+SO_PATH = os.environ.get("HUFFB200_SO") or os.path.join(HERE, "libhuffb200.so")   # override: experiment builds
 
 HB_MAX_LEAVES = 257
 HB_MAX_NODES = 2 * HB_MAX_LEAVES - 1

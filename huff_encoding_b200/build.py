@@ -26,17 +26,23 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines: list[str] | None = None, out: str | None = None) -> str:
+    """defines / out: experiment builds (e.g. defines=["HB_LOOKBACK_BITS=128"], out="libhuffb200_lb128.so"),
+    selected at run time with HUFFB200_SO=<path>."""
+    target = os.path.join(HERE, out) if out else SO
+    if not force and not defines and not out and not needs_build():
         return SO
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + [os.path.join(CSRC, f) for f in SOURCES]
+    cmd = [NVCC] + FLAGS + [f"-D{d}" for d in (defines or [])] + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", target] + [os.path.join(CSRC, f) for f in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode:
         raise RuntimeError("nvcc failed building libhuffb200.so")
-    return SO
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -440,8 +440,8 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
     for (int round = 0; round < 2; round++) {
         HB_CUDA(cudaMemsetAsync(ctx->d_n_dirty, 0, sizeof(uint32_t), ctx->stream));
         hb::dec_verify_kernel<<<static_cast<unsigned>((n_blocks + 255) / 256), 256, 0, ctx->stream>>>(p, ctx->dirty.p, ctx->d_n_dirty);
-        hb::dec_scan_groups_kernel<<<n_groups, hb::kDecThreads, 0, ctx->stream>>>(ctx->blk_count.p, p.n_blocks, ctx->blk_local.p, ctx->group_total.p);
-        hb::dec_scan_totals_kernel<<<1, hb::kDecThreads, 0, ctx->stream>>>(ctx->group_total.p, n_groups, d_grand);
+        hb::dec_scan_groups_kernel<<<n_groups, hb::kScanThreads, 0, ctx->stream>>>(ctx->blk_count.p, p.n_blocks, ctx->blk_local.p, ctx->group_total.p);
+        hb::dec_scan_totals_kernel<<<1, hb::kScanThreads, 0, ctx->stream>>>(ctx->group_total.p, n_groups, d_grand);
         dec_collect_kernel<<<1, 1, 0, ctx->stream>>>(p, d_grand, ctx->d_n_dirty, ctx->d_dec_result);
         ctx->launches += 4;
         HB_CUDA(cudaGetLastError());

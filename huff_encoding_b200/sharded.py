@@ -52,7 +52,7 @@ class ShardedCodec:
             h = local.cpu().numpy().astype(np.uint64)[None, :]
         global_w = h.sum(axis=0)
         tree = eng.tree_from_weights(global_w)
-        lens = np.array([tree.raw.code_len[b] for b in range(256)], dtype=np.uint64)
+        lens = np.frombuffer(tree.raw.code_len, dtype=np.uint16).astype(np.uint64)
         all_bits = [int(x) for x in (h * lens[None, :]).sum(axis=1)]
         my_bits = all_bits[self.rank]
         offset = sum(all_bits[: self.rank])
@@ -93,6 +93,17 @@ class ShardedCodec:
         return n
 
     def round_trip(self, data, comp_buf, out_buf, want_events: bool = False):
+        if self.world == 1 and not want_events:
+            # single GPU: the whole of compress() / decompress() runs inside the library (histogram -> host tree ->
+            # encode, count -> write), no Python between the kernels
+            _, clen, pad, tree = self.eng.compress(data, out=comp_buf)
+            _, n = self.eng.decompress(comp_buf, clen, pad, tree, out=out_buf)
+            raw = tree.raw
+            self.last_info = {"fixed_len": raw.max_len if (raw.min_len == raw.max_len and raw.max_len in (1, 2, 4, 8)) else 0,
+                              "tree": tree, "bits": clen * 8 - pad, "bit_offset": 0, "start_bit": 0, "comp_len": clen,
+                              "total_bits": clen * 8 - pad, "padding_bits": pad, "all_bits": [clen * 8 - pad],
+                              "n_letters": n}
+            return None
         marks = {} if want_events else None
         info = self.compress(data, comp_buf, marks)
         self.decompress(comp_buf, info, out_buf, marks)

@@ -69,6 +69,7 @@ SYMBOLS = [
     ("hb_ctx_sync", C.c_int, [_vp]),
     ("hb_ctx_stream", _vp, [_vp]),
     ("hb_ctx_kernel_launches", C.c_int, [_vp, _u64p]),
+    ("hb_ctx_last_decode_repairs", C.c_int, [_vp, C.POINTER(C.c_uint32)]),
     ("hb_free", None, [_vp]),
     ("hb_host_alloc", C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     ("hb_host_free", None, [_vp]),

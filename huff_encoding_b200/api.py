@@ -127,6 +127,11 @@ class Context:
     def sync(self):
         _raise(self._lib.hb_ctx_sync(self._h))
 
+    def last_decode_repairs(self) -> int:
+        n = C.c_uint32(0)
+        _raise(self._lib.hb_ctx_last_decode_repairs(self._h, C.byref(n)))
+        return n.value
+
     def stream(self) -> int:
         return int(self._lib.hb_ctx_stream(self._h) or 0)
 

@@ -107,6 +107,8 @@ struct hb_ctx {
     DecResult *h_dec_result = nullptr;   // pinned
     uint32_t *d_n_dirty = nullptr;
     int dec_count_grid = 0, dec_write_grid = 0;
+    bool spoil_speculation = false;      // HB_DEBUG_SPOIL_SPECULATION=1 (tests): force the cross-CTA repair path
+    uint32_t last_repairs = 0;           // chunks repaired by dec_fix_kernel in the last count pass
     int cnt_bits = 13;                   // HB_CNT_BITS=12|13|14: index width of the multi-letter count table (13 measured best)
     hb::DecParams last_dec;
     uint64_t last_dec_total = 0;
@@ -420,6 +422,8 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
     p.fixed_len = (tree->min_len == tree->max_len) ? tree->max_len : 0;
     p.max_len = tree->max_len ? tree->max_len : 1;
     p.cnt_bits = static_cast<uint32_t>(ctx->cnt_bits);
+    p.spoil_speculation = ctx->spoil_speculation ? 1u : 0u;
+    ctx->last_repairs = 0;
     if (tree->nodes[tree->root].left == HB_NO_CHILD) { p.fixed_len = 1; p.len_gcd = 1; }
     p.first_block = static_cast<uint32_t>(first_block);
     p.n_blocks = static_cast<uint32_t>(n_blocks);
@@ -448,6 +452,7 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
         HB_CUDA(cudaMemcpyAsync(ctx->h_dec_result, ctx->d_dec_result, sizeof(DecResult), cudaMemcpyDeviceToHost, ctx->stream));
         HB_CUDA(cudaStreamSynchronize(ctx->stream));
         if (ctx->h_dec_result->n_dirty == 0) break;
+        ctx->last_repairs += ctx->h_dec_result->n_dirty;
         if (round == 1) { g_last_error = "decoder chain repair did not converge"; return HB_ERR_CUDA; }
         // rare: a chunk whose speculative entry was wrong even after a 1024-bit look-back -> serial repair
         if (ctx->cnt_bits == 14) hb::dec_fix_kernel<14><<<1, hb::kDecThreads, smem_count, ctx->stream>>>(p, ctx->d_dec_tables, ctx->dirty.p);
@@ -553,6 +558,7 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
         HB_CUDA(cudaMalloc(&ctx->d_fix_enc, 256));
         HB_CUDA(cudaMalloc(&ctx->d_fix_dec, 256));
         { const char *nf = std::getenv("HB_NO_FASTPATH"); ctx->fastpath = !(nf && nf[0] == '1'); }
+        { const char *sp = std::getenv("HB_DEBUG_SPOIL_SPECULATION"); ctx->spoil_speculation = sp && sp[0] == '1'; }
         HB_CUDA(cudaMalloc(&ctx->d_dec_result, sizeof(DecResult)));
         HB_CUDA(cudaMalloc(&ctx->d_n_dirty, sizeof(uint32_t)));
         HB_CUDA(cudaMallocHost(&ctx->h_dec_result, sizeof(DecResult)));
@@ -612,6 +618,12 @@ hb_status hb_ctx_sync(hb_ctx *ctx) {
 }
 
 void *hb_ctx_stream(hb_ctx *ctx) { return ctx ? static_cast<void *>(ctx->stream) : nullptr; }
+
+hb_status hb_ctx_last_decode_repairs(hb_ctx *ctx, uint32_t *count) {
+    if (!ctx || !count) return HB_ERR_INVALID_ARG;
+    *count = ctx->last_repairs;
+    return HB_OK;
+}
 
 hb_status hb_ctx_kernel_launches(hb_ctx *ctx, uint64_t *count) {
     if (!ctx || !count) return HB_ERR_INVALID_ARG;

@@ -82,6 +82,7 @@ struct DecParams {
     uint32_t len_gcd, fixed_len;       // gcd of code lengths; fixed_len != 0 when all codes have that length
     uint32_t max_len;                  // longest code (bounds how far a thread may read past its subsequence)
     uint32_t cnt_bits;                 // index width of DecTables::cnt in use (12..14)
+    uint32_t spoil_speculation;        // test hook: CTA-leading threads skip their look-back (forces the repair path)
     uint32_t first_block, n_blocks;    // CTAs cover chunks first_block .. first_block + n_blocks - 1
     uint32_t *sub_info;                // per subsequence (relative to first_block): entry_rel << 16 | count
     uint64_t *blk_entry, *blk_exit;    // per CTA, absolute buffer bits (kEnd64 = none)
@@ -343,6 +344,7 @@ __device__ void dec_count_block(const DecParams &p, uint32_t blk, uint64_t entry
         } else {
             uint32_t window = (t == 0 || is_first) ? static_cast<uint32_t>(kHaloWords * 32) : static_cast<uint32_t>(kLookbackBits);
             if (p.fixed_len) window = 0;
+            if (p.spoil_speculation && t == 0 && !is_first) window = 0;   // deliberately bad guess (tests only)
             uint32_t q0 = q_lo > window ? q_lo - window : 0;
             if (q0 < q_buf0) q0 = q_buf0;
             if (p.len_gcd > 1) {           // align to the phase of the stream: (stream_bit0 + abs) % gcd == 0

@@ -89,6 +89,9 @@ hb_status hb_ctx_destroy(hb_ctx *ctx);
 hb_status hb_ctx_sync(hb_ctx *ctx);
 void     *hb_ctx_stream(hb_ctx *ctx);            /* the cudaStream_t every *_dev call is enqueued on */
 hb_status hb_ctx_kernel_launches(hb_ctx *ctx, uint64_t *count);   /* kernels launched so far (bench.py's gpu_launches) */
+/* number of 32 KiB chunks whose speculative entry was refuted and repaired in the last decode count pass (normally 0;
+ * HB_DEBUG_SPOIL_SPECULATION=1 at ctx creation makes the speculation deliberately bad so tests can reach that path) */
+hb_status hb_ctx_last_decode_repairs(hb_ctx *ctx, uint32_t *count);
 void      hb_free(void *p);                      /* frees buffers returned by *_u8 calls */
 /* pinned host staging for callers that want full PCIe speed on the *_u8 path */
 hb_status hb_host_alloc(size_t bytes, void **p);

@@ -392,3 +392,22 @@ def test_n2_cli_file_round_trip(hb, tmp_path):
     assert cli.main(["-d", "-n", str(hff), str(out)]) == 0
     assert np.array_equal(np.fromfile(out, dtype=np.uint8), data)
     assert cli.parse_block_size("2G") == 2_000_000_000 and cli.parse_block_size("4Ki") == 4096
+
+
+def test_cross_chunk_repair_path_when_speculation_is_wrong(hb):
+    # the serial repair kernel only runs when a chunk's 1024-bit look-back fails to resynchronise, which real code sets
+    # practically never do; the debug switch makes every chunk-leading thread guess without look-back instead
+    import os
+    os.environ["HB_DEBUG_SPOIL_SPECULATION"] = "1"
+    try:
+        ctx = hb.Context(0)
+    finally:
+        del os.environ["HB_DEBUG_SPOIL_SPECULATION"]
+    for gen, n in (("zipf", 3_000_017), ("english", 2_500_003)):
+        data = getattr(G, gen)(n)
+        comp, pad, tree = O.compress(data)
+        ours = hb.HuffTree.from_weights(hb.build_weights_map(data, ctx=ctx))
+        got = hb.decompress(hb.CompressData(comp, pad, ours), ctx=ctx)
+        assert np.array_equal(got, data), _first_diff(got, data)
+        assert ctx.last_decode_repairs() > 10, "the repair path was not exercised"
+    ctx.close()

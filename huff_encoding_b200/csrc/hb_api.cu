@@ -114,8 +114,11 @@ struct hb_ctx {
     uint64_t last_dec_total = 0;
     bool last_dec_valid = false;
 
-    // staging for the host-buffer API
+    // staging for the host-buffer API; two copy streams + events to overlap H2D / kernel / D2H by chunks
     DevBuf<uint8_t> stage_in, stage_out;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    static constexpr int kPipeEvents = 64;
+    cudaEvent_t ev_in[kPipeEvents] = {}, ev_k[kPipeEvents] = {};
     uint64_t *h_hist = nullptr;          // pinned 256 x u64
     unsigned long long *h_total_bits = nullptr;
 };
@@ -550,6 +553,12 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     hb_status rc = [&]() -> hb_status {
         HB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        HB_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        HB_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < hb_ctx::kPipeEvents; i++) {
+            HB_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+            HB_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+        }
         HB_CUDA(cudaMalloc(&ctx->d_hist, 256 * sizeof(unsigned long long)));
         HB_CUDA(cudaMalloc(&ctx->d_region_hist, static_cast<size_t>(ctx->sm_count) * 256 * sizeof(uint32_t)));
         HB_CUDA(cudaMalloc(&ctx->d_enc_table, sizeof(hb::EncTable)));
@@ -606,6 +615,12 @@ hb_status hb_ctx_destroy(hb_ctx *ctx) {
     ctx->sub_info.release(); ctx->blk_count.release(); ctx->blk_local.release(); ctx->dirty.release();
     ctx->blk_entry.release(); ctx->blk_exit.release(); ctx->group_total.release();
     ctx->stage_in.release(); ctx->stage_out.release();
+    for (int i = 0; i < hb_ctx::kPipeEvents; i++) {
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
+    }
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return HB_OK;
@@ -784,6 +799,46 @@ hb_status hb_compress_with_tree_u8(hb_ctx *ctx, const uint8_t *data, size_t n, c
     return compress_host_common(ctx, data, n, tree, 0, nullptr, comp_bytes, nullptr, 0, comp_len, padding_bits, missing);
 }
 
+// Fixed-length code set, host buffers: every chunk of the stream decodes independently, so the H2D copy of chunk
+// i+1, the translation kernel of chunk i and the D2H copy of chunk i-1 run concurrently (full-duplex PCIe).
+static hb_status decompress_host_fixed_pipelined(hb_ctx *ctx, const uint8_t *comp, size_t comp_len, uint64_t total_bits,
+                                                 uint8_t *host, size_t n_letters) {
+    const uint32_t L = ctx->dec_fixed_len;
+    const size_t per = 8 / L;                                        // letters per stream byte
+    const size_t in_bytes = (n_letters * L + 7) / 8;
+    (void)comp_len; (void)total_bits;
+    HB_TRY(ctx->stage_in.reserve(in_bytes + 64));
+    HB_TRY(ctx->stage_out.reserve(n_letters + 64));
+    size_t chunk = std::max<size_t>((in_bytes + hb_ctx::kPipeEvents - 1) / hb_ctx::kPipeEvents, static_cast<size_t>(32) << 20);
+    chunk = (chunk + 255) / 256 * 256;
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));                     // the table upload precedes every kernel below
+    int i = 0;
+    for (size_t off = 0; off < in_bytes; off += chunk, i++) {
+        const size_t len = std::min(chunk, in_bytes - off);
+        const size_t letters = std::min(len * per, n_letters - off * per);
+        HB_CUDA(cudaMemcpyAsync(ctx->stage_in.p + off, comp + off, len, cudaMemcpyHostToDevice, ctx->s_h2d));
+        HB_CUDA(cudaEventRecord(ctx->ev_in[i], ctx->s_h2d));
+        HB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
+        if (L == 8) {
+            const size_t blocks = (letters / 16 + hb::kFixThreads - 1) / hb::kFixThreads;
+            const int grid = static_cast<int>(std::max<size_t>(1, std::min<size_t>(ctx->fix_grid, blocks)));
+            hb::fixed8_translate_kernel<<<grid, hb::kFixThreads, 0, ctx->stream>>>(ctx->stage_in.p + off, ctx->stage_out.p + off, letters, ctx->d_fix_dec);
+        } else {
+            const size_t blocks = (len + hb::kFixThreads - 1) / hb::kFixThreads;
+            const int grid = static_cast<int>(std::max<size_t>(1, std::min<size_t>(ctx->fix_grid * 4, blocks)));
+            hb::fixed_unpack_kernel<<<grid, hb::kFixThreads, 0, ctx->stream>>>(ctx->stage_in.p + off, ctx->stage_out.p + off * per, letters, L, ctx->d_fix_dec);
+        }
+        ctx->launches++;
+        HB_CUDA(cudaGetLastError());
+        HB_CUDA(cudaEventRecord(ctx->ev_k[i], ctx->stream));
+        HB_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[i], 0));
+        HB_CUDA(cudaMemcpyAsync(host + off * per, ctx->stage_out.p + off * per, letters, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    }
+    HB_CUDA(cudaStreamSynchronize(ctx->s_d2h));
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return HB_OK;
+}
+
 static hb_status decompress_host_common(hb_ctx *ctx, const uint8_t *comp, size_t comp_len, uint8_t padding_bits,
                                         const hb_tree *tree, uint8_t **out, uint8_t *dst, size_t cap, size_t *out_n) {
     if (out) *out = nullptr;
@@ -791,9 +846,23 @@ static hb_status decompress_host_common(hb_ctx *ctx, const uint8_t *comp, size_t
     if (comp_len == 0) return HB_ERR_EMPTY_COMP;
     if (padding_bits > 7) return HB_ERR_BAD_PADDING;
     if (!comp) return HB_ERR_INVALID_ARG;
+    const uint64_t total_bits = static_cast<uint64_t>(comp_len) * 8 - padding_bits;
+    HB_TRY(upload_dec_tables(ctx, tree));
+    if (ctx->dec_fixed_len) {
+        const size_t n = static_cast<size_t>(total_bits / ctx->dec_fixed_len);   // trailing bits that complete no code are dropped
+        if (dst && n > cap) { *out_n = n; return HB_ERR_CAPACITY; }
+        uint8_t *host = dst ? dst : static_cast<uint8_t *>(std::malloc(n ? n : 1));
+        if (!host) return HB_ERR_NO_MEM;
+        if (n) {
+            hb_status rc = decompress_host_fixed_pipelined(ctx, comp, comp_len, total_bits, host, n);
+            if (rc != HB_OK) { if (!dst) std::free(host); return rc; }
+        }
+        if (out) *out = host;
+        *out_n = n;
+        return HB_OK;
+    }
     HB_TRY(ctx->stage_in.reserve(comp_len + 16));
     HB_CUDA(cudaMemcpyAsync(ctx->stage_in.p, comp, comp_len, cudaMemcpyHostToDevice, ctx->stream));
-    const uint64_t total_bits = static_cast<uint64_t>(comp_len) * 8 - padding_bits;
     hb_shard_info info;
     HB_TRY(run_count_pass(ctx, ctx->stage_in.p, total_bits, 0, total_bits, 0, 0, tree, &info));
     const size_t n = static_cast<size_t>(info.n_letters);

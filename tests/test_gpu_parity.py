@@ -411,3 +411,17 @@ def test_cross_chunk_repair_path_when_speculation_is_wrong(hb):
         assert np.array_equal(got, data), _first_diff(got, data)
         assert ctx.last_decode_repairs() > 10, "the repair path was not exercised"
     ctx.close()
+
+
+def test_host_api_pipelined_fixed_length_decode_multi_chunk(hb):
+    # > 32 MiB of stream: hb_decompress_u8 overlaps H2D / translation / D2H chunk by chunk (fixed-length code sets)
+    for mask, n in ((255, (80 << 20) + 7), (15, (90 << 20) + 5)):
+        data = (G.uniform(n, seed=mask) & mask).astype(np.uint8)
+        cd = hb.compress(data)
+        assert len(set(len(c) for c in cd.huff_tree().read_codes().values())) == 1
+        assert cd.comp_bytes().size > (32 << 20)
+        back = hb.decompress(cd)
+        assert np.array_equal(back, data), _first_diff(back, data)
+        out = np.empty(n + 3, dtype=np.uint8)                      # caller-owned buffer variant
+        back2 = hb.decompress(cd, out=out)
+        assert back2.size == n and np.array_equal(back2, data)

@@ -26,6 +26,7 @@ class ShardedCodec:
     def __init__(self, engine, world: int = 1, rank: int = 0, dist=None):
         self.eng, self.world, self.rank, self.dist = engine, world, rank, dist
         self.last_info = None
+        self._gathered = None
 
     # ------------------------------------------------------------ helpers
     def _event(self):
@@ -45,9 +46,15 @@ class ShardedCodec:
             # ONE exchange: all-gather the G local histograms (G x 2 KiB).  Every rank sums them into the global
             # histogram (= the all-reduce) and, once the tree is known, also knows every shard's bit total
             # (= the all-gather of totals + exclusive scan) without a second collective.
-            parts = [torch.zeros_like(local) for _ in range(self.world)]
-            dist.all_gather(parts, local)
-            h = torch.stack(parts).cpu().numpy().astype(np.uint64)      # host sync: the tree needs the histogram
+            if self._gathered is None:
+                self._gathered = torch.zeros(self.world, 256, dtype=local.dtype, device=local.device)
+            try:
+                dist.all_gather_into_tensor(self._gathered, local)
+            except Exception:                                           # backends without the flat variant (gloo)
+                parts = [torch.zeros_like(local) for _ in range(self.world)]
+                dist.all_gather(parts, local)
+                self._gathered.copy_(torch.stack(parts))
+            h = self._gathered.cpu().numpy().astype(np.uint64)          # host sync: the tree needs the histogram
         else:
             h = local.cpu().numpy().astype(np.uint64)[None, :]
         global_w = h.sum(axis=0)

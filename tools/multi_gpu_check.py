@@ -26,29 +26,38 @@ shard = getattr(G, kind)(hi - lo, offset=lo, device=dev)
 comp_buf = torch.zeros(shard.numel() + shard.numel() // 4 + 4096, dtype=torch.uint8, device=dev)
 with torch.cuda.stream(eng.stream):
     info = codec.compress(shard, comp_buf)
-    gathered = codec.gather_stream(comp_buf, info)
     out_buf = torch.zeros(shard.numel() + 64, dtype=torch.uint8, device=dev)
     n = codec.decompress(comp_buf, info, out_buf)
     eng.sync()
 assert n == shard.numel() and torch.equal(out_buf[:n], shard), "shard round trip failed"
-if rank == 0:
-    stream, pad = gathered
-    full = getattr(G, kind)(n_total, device=dev)
-    one, clen, pad1, tree1 = Engine(local).compress(full)
-    assert clen == stream.size and pad1 == pad, (clen, stream.size, pad1, pad)
-    assert np.array_equal(one[:clen].cpu().numpy(), stream), "concatenated shards differ from the single-GPU stream"
-    assert tree1.read_codes() == info["tree"].read_codes()
-    ref = torch.from_numpy(stream).to(dev)
-else:
-    ref = None
-# byte-sharded decode of the gathered stream (speculative entries + neighbour verification)
+del out_buf
+torch.cuda.synchronize()
+# concatenate the shard streams ON THE DEVICE of rank 0 (OR-merge of the byte two shards share) and compare with the
+# stream one GPU produces for the whole input
 total_bits = info["total_bits"]
 n_bytes = (total_bits + 7) // 8
+cap = max((b + 7) // 8 + 2 for b in info["all_bits"])
+send = torch.zeros(cap, dtype=torch.uint8, device=dev)
+send[: info["comp_len"]] = comp_buf[: info["comp_len"]]
+recv = [torch.zeros(cap, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+dist.gather(send, recv, dst=0)
+pad4 = torch.zeros(((n_bytes + 15) // 16) * 16 + 4096, dtype=torch.uint8, device=dev)
 if rank == 0:
-    pad4 = torch.zeros(((n_bytes + 15) // 16) * 16 + 4096, dtype=torch.uint8, device=dev)
-    pad4[:n_bytes] = ref
-else:
-    pad4 = torch.zeros(((n_bytes + 15) // 16) * 16 + 4096, dtype=torch.uint8, device=dev)
+    off = 0
+    for g in range(world):
+        ln = (off % 8 + info["all_bits"][g] + 7) // 8
+        pad4[off // 8: off // 8 + ln] |= recv[g][:ln]
+        off += info["all_bits"][g]
+    del recv
+    full = getattr(G, kind)(n_total, device=dev)
+    one, clen, pad1, tree1 = Engine(local).compress(full)
+    del full
+    assert clen == n_bytes and pad1 == info["padding_bits"], (clen, n_bytes, pad1, info["padding_bits"])
+    assert torch.equal(one[:clen], pad4[:n_bytes]), "concatenated shards differ from the single-GPU stream"
+    assert tree1.read_codes() == info["tree"].read_codes()
+    del one
+torch.cuda.synchronize()
+# byte-sharded decode of the gathered stream (speculative entries + neighbour verification)
 dist.broadcast(pad4, src=0)
 cut = [n_bytes * g // world // 16 * 16 for g in range(world)] + [n_bytes]
 b0 = max(cut[rank] - 4096, 0)

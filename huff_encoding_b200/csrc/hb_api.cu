@@ -125,11 +125,23 @@ struct hb_ctx {
 
 namespace {
 
-hb_status check_ctx(hb_ctx *ctx) {
-    if (!ctx) return HB_ERR_INVALID_ARG;
-    HB_CUDA(cudaSetDevice(ctx->device));
-    return HB_OK;
-}
+// Makes the ctx's device current for the duration of an API call and restores the caller's device afterwards
+// (the host application -- e.g. torch -- keeps its own notion of the current device).
+struct DeviceScope {
+    int prev = -1;
+    bool switched = false;
+    hb_status enter(hb_ctx *ctx) {
+        if (!ctx) return HB_ERR_INVALID_ARG;
+        HB_CUDA(cudaGetDevice(&prev));
+        if (prev != ctx->device) {
+            HB_CUDA(cudaSetDevice(ctx->device));
+            switched = true;
+        }
+        return HB_OK;
+    }
+    ~DeviceScope() { if (switched) cudaSetDevice(prev); }
+};
+#define HB_ENTER(ctx) DeviceScope hb_scope_; HB_TRY(hb_scope_.enter(ctx))
 
 bool same_codes(const hb_tree &a, const hb_tree &b) {
     return std::memcmp(a.has_code, b.has_code, sizeof a.has_code) == 0 &&
@@ -540,6 +552,9 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
     int count = 0;
     HB_CUDA(cudaGetDeviceCount(&count));
     if (device < 0 || device >= count) { g_last_error = "no such CUDA device"; return HB_ERR_CUDA; }
+    int prev_dev = -1;
+    HB_CUDA(cudaGetDevice(&prev_dev));
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
     HB_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     HB_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -605,6 +620,9 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
 
 hb_status hb_ctx_destroy(hb_ctx *ctx) {
     if (!ctx) return HB_OK;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_hist); cudaFree(ctx->d_region_hist); cudaFree(ctx->d_enc_table); cudaFree(ctx->d_total_bits); cudaFree(ctx->d_dec_tables); cudaFree(ctx->d_fix_enc); cudaFree(ctx->d_fix_dec);
@@ -627,7 +645,7 @@ hb_status hb_ctx_destroy(hb_ctx *ctx) {
 }
 
 hb_status hb_ctx_sync(hb_ctx *ctx) {
-    HB_TRY(check_ctx(ctx));
+    HB_ENTER(ctx);
     HB_CUDA(cudaStreamSynchronize(ctx->stream));
     return HB_OK;
 }
@@ -657,14 +675,14 @@ void hb_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 // ---------------------------------------------------------------- device-buffer API
 hb_status hb_histogram_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, uint64_t *d_hist256) {
-    HB_TRY(check_ctx(ctx));
+    HB_ENTER(ctx);
     if (!d_hist256 || (n && !d_data)) return HB_ERR_INVALID_ARG;
     return launch_hist(ctx, d_data, n, reinterpret_cast<unsigned long long *>(d_hist256));
 }
 
 hb_status hb_encode_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, const hb_tree *tree, uint32_t start_bit,
                            uint8_t *d_out, size_t out_cap, uint64_t *d_total_bits) {
-    HB_TRY(check_ctx(ctx));
+    HB_ENTER(ctx);
     if (!tree || !d_out || (n && !d_data) || start_bit > 31) return HB_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(d_data) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 3)) return HB_ERR_INVALID_ARG;
     (void)out_cap;   // capacity is the caller's contract (exact size comes from hb_stream_bits); checked in the *_u8 path
@@ -675,7 +693,7 @@ hb_status hb_encode_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, const h
 
 hb_status hb_compress_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, int order_mode, hb_tree *tree_out,
                              uint8_t *d_out, size_t out_cap, size_t *comp_len, uint8_t *padding_bits) {
-    HB_TRY(check_ctx(ctx));
+    HB_ENTER(ctx);
     if (!tree_out || !d_out || !comp_len || !padding_bits || (n && !d_data)) return HB_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(d_data) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 3)) return HB_ERR_INVALID_ARG;
     if (n == 0) return HB_ERR_EMPTY_WEIGHTS;                      // comp.rs:354 -> tree_inner.rs:283-285
@@ -696,20 +714,20 @@ hb_status hb_compress_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, int o
 
 hb_status hb_decode_count_dev(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits, uint64_t own_begin,
                               uint64_t own_end, uint64_t stream_bit0, const hb_tree *tree, hb_shard_info *info) {
-    HB_TRY(check_ctx(ctx));
+    HB_ENTER(ctx);
     if (!d_buf || !tree || !info) return HB_ERR_INVALID_ARG;
     return run_count_pass(ctx, d_buf, avail_bits, own_begin, own_end, info->entry_bit, stream_bit0, tree, info);
 }
 
 hb_status hb_decode_write_dev(hb_ctx *ctx, uint8_t *d_out, size_t out_cap) {
-    HB_TRY(check_ctx(ctx));
+    HB_ENTER(ctx);
     if (!d_out && ctx->last_dec_total) return HB_ERR_INVALID_ARG;
     return run_write_pass(ctx, d_out, out_cap);
 }
 
 hb_status hb_decompress_u8_dev(hb_ctx *ctx, const uint8_t *d_comp, size_t comp_len, uint8_t padding_bits,
                                const hb_tree *tree, uint8_t *d_out, size_t out_cap, size_t *out_n) {
-    HB_TRY(check_ctx(ctx));
+    HB_ENTER(ctx);
     if (!tree || !out_n) return HB_ERR_INVALID_ARG;
     if (comp_len == 0) return HB_ERR_EMPTY_COMP;                  // comp.rs:56-58
     if (padding_bits > 7) return HB_ERR_BAD_PADDING;              // comp.rs:59-61
@@ -728,7 +746,7 @@ hb_status hb_decompress_u8_dev(hb_ctx *ctx, const uint8_t *d_comp, size_t comp_l
 
 // ---------------------------------------------------------------- host-buffer API
 hb_status hb_histogram_u8(hb_ctx *ctx, const uint8_t *data, size_t n, uint64_t out[256]) {
-    HB_TRY(check_ctx(ctx));
+    HB_ENTER(ctx);
     if (!out || (n && !data)) return HB_ERR_INVALID_ARG;
     HB_TRY(ctx->stage_in.reserve(n + 16));
     if (n) HB_CUDA(cudaMemcpyAsync(ctx->stage_in.p, data, n, cudaMemcpyHostToDevice, ctx->stream));
@@ -785,7 +803,7 @@ static hb_status compress_host_common(hb_ctx *ctx, const uint8_t *data, size_t n
 
 hb_status hb_compress_u8(hb_ctx *ctx, const uint8_t *data, size_t n, int order_mode, hb_tree *tree_out,
                          uint8_t **comp_bytes, size_t *comp_len, uint8_t *padding_bits) {
-    HB_TRY(check_ctx(ctx));
+    HB_ENTER(ctx);
     if (!tree_out || !comp_bytes || !comp_len || !padding_bits || (n && !data)) return HB_ERR_INVALID_ARG;
     if (n == 0) return HB_ERR_EMPTY_WEIGHTS;
     return compress_host_common(ctx, data, n, nullptr, order_mode, tree_out, comp_bytes, nullptr, 0, comp_len, padding_bits, nullptr);
@@ -793,7 +811,7 @@ hb_status hb_compress_u8(hb_ctx *ctx, const uint8_t *data, size_t n, int order_m
 
 hb_status hb_compress_with_tree_u8(hb_ctx *ctx, const uint8_t *data, size_t n, const hb_tree *tree,
                                    uint8_t **comp_bytes, size_t *comp_len, uint8_t *padding_bits, uint8_t *missing) {
-    HB_TRY(check_ctx(ctx));
+    HB_ENTER(ctx);
     if (!tree || !comp_bytes || !comp_len || !padding_bits || (n && !data)) return HB_ERR_INVALID_ARG;
     if (n == 0) return HB_ERR_EMPTY_COMP;                         // empty letters -> CompressData::new panics (comp.rs:56-58)
     return compress_host_common(ctx, data, n, tree, 0, nullptr, comp_bytes, nullptr, 0, comp_len, padding_bits, missing);
@@ -884,21 +902,21 @@ static hb_status decompress_host_common(hb_ctx *ctx, const uint8_t *comp, size_t
 
 hb_status hb_decompress_u8(hb_ctx *ctx, const uint8_t *comp, size_t comp_len, uint8_t padding_bits,
                            const hb_tree *tree, uint8_t **out, size_t *out_n) {
-    HB_TRY(check_ctx(ctx));
+    HB_ENTER(ctx);
     if (!tree || !out || !out_n) return HB_ERR_INVALID_ARG;
     return decompress_host_common(ctx, comp, comp_len, padding_bits, tree, out, nullptr, 0, out_n);
 }
 
 hb_status hb_decompress_u8_into(hb_ctx *ctx, const uint8_t *comp, size_t comp_len, uint8_t padding_bits,
                                 const hb_tree *tree, uint8_t *out, size_t out_cap, size_t *out_n) {
-    HB_TRY(check_ctx(ctx));
+    HB_ENTER(ctx);
     if (!tree || !out || !out_n) return HB_ERR_INVALID_ARG;
     return decompress_host_common(ctx, comp, comp_len, padding_bits, tree, nullptr, out, out_cap, out_n);
 }
 
 hb_status hb_compress_u8_into(hb_ctx *ctx, const uint8_t *data, size_t n, int order_mode, hb_tree *tree_out,
                               uint8_t *comp_bytes, size_t comp_cap, size_t *comp_len, uint8_t *padding_bits) {
-    HB_TRY(check_ctx(ctx));
+    HB_ENTER(ctx);
     if (!tree_out || !comp_bytes || !comp_len || !padding_bits || (n && !data)) return HB_ERR_INVALID_ARG;
     if (n == 0) return HB_ERR_EMPTY_WEIGHTS;
     return compress_host_common(ctx, data, n, nullptr, order_mode, tree_out, nullptr, comp_bytes, comp_cap, comp_len, padding_bits, nullptr);
@@ -907,7 +925,7 @@ hb_status hb_compress_u8_into(hb_ctx *ctx, const uint8_t *data, size_t n, int or
 hb_status hb_compress_with_tree_u8_into(hb_ctx *ctx, const uint8_t *data, size_t n, const hb_tree *tree,
                                         uint8_t *comp_bytes, size_t comp_cap, size_t *comp_len, uint8_t *padding_bits,
                                         uint8_t *missing) {
-    HB_TRY(check_ctx(ctx));
+    HB_ENTER(ctx);
     if (!tree || !comp_bytes || !comp_len || !padding_bits || (n && !data)) return HB_ERR_INVALID_ARG;
     if (n == 0) return HB_ERR_EMPTY_COMP;
     return compress_host_common(ctx, data, n, tree, 0, nullptr, nullptr, comp_bytes, comp_cap, comp_len, padding_bits, missing);

@@ -311,6 +311,26 @@ def run_ours(args):
                    "comp_bytes": zc, "phase_ms": {k: round(v, 4) for k, v in gphase.items()},
                    "alg_bytes": {"hist": n, "encode": n + zc, "dec_count": zc, "dec_write": zc + n}}
         del zdata
+        # the same uniform input forced through the general kernels (fast path off): what configs[1] costs without it
+        os.environ["HB_NO_FASTPATH"] = "1"
+        try:
+            eng2 = Engine(local_rank)
+        finally:
+            del os.environ["HB_NO_FASTPATH"]
+        codec2 = ShardedCodec(eng2, world, rank, dist if world > 1 else None)
+        uphase = {k: 0.0 for k in phases}
+        with torch.cuda.stream(eng2.stream):
+            for _ in range(2):
+                codec2.round_trip(data, comp_buf, out_buf, want_events=True)
+            eng2.stream.synchronize()
+            um = [codec2.round_trip(data, comp_buf, out_buf, want_events=True) for _ in range(gsteps)]
+            eng2.stream.synchronize()
+        assert torch.equal(out_buf[:n], data), "forced general-path round trip mismatch"
+        for m in um:
+            for k in phases:
+                uphase[k] += m[k][0].elapsed_time(m[k][1]) / gsteps
+        general["uniform_forced_general_phase_ms"] = {k: round(v, 4) for k, v in uphase.items()}
+        del codec2, eng2
         codec.round_trip(data, comp_buf, out_buf)      # restore last_info for the headline workload
         info = codec.last_info
 

@@ -15,7 +15,26 @@ namespace hb {
 
 constexpr int kFixThreads = 512;
 
+#ifndef HB_FIX_UNROLL
+#define HB_FIX_UNROLL 4
+#endif
+
+struct u32x8 { uint32_t v[8]; };
+__device__ __forceinline__ u32x8 ld_stream_256(const void *p) {
+    u32x8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_256(void *p, const u32x8 &r) {
+    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
+                 : "memory");
+}
+
 // L == 8: out[i] = table[in[i]] for n bytes; table lane-replicated in shared memory ([256][32] u32, conflict-free).
+// in / out 32-byte aligned -> 256-bit loads and stores (one full sector per lane); else 128-bit.
 __global__ void __launch_bounds__(kFixThreads)
 fixed8_translate_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n,
                         const uint8_t *__restrict__ table) {
@@ -27,25 +46,52 @@ fixed8_translate_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ ou
         return my[(w & 0xFFu) << 5] | (my[((w >> 8) & 0xFFu) << 5] << 8) | (my[((w >> 16) & 0xFFu) << 5] << 16) |
                (my[(w >> 24) << 5] << 24);
     };
-    const size_t n_vec = n / 16;
-    const uint4 *src = reinterpret_cast<const uint4 *>(in);
-    uint4 *dst = reinterpret_cast<uint4 *>(out);
     const size_t stride = static_cast<size_t>(gridDim.x) * kFixThreads;
     size_t i = static_cast<size_t>(blockIdx.x) * kFixThreads + threadIdx.x;
-    for (; i + 3 * stride < n_vec; i += 4 * stride) {
-        uint4 v[4];
+    size_t done = 0;                                           // bytes handled by the vector loops
+#ifndef HB_FIX_NO_V8
+    if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 31) == 0) {
+        const size_t n_vec = n / 32;
+        for (; i + (HB_FIX_UNROLL - 1) * stride < n_vec; i += HB_FIX_UNROLL * stride) {
+            u32x8 v[HB_FIX_UNROLL];
 #pragma unroll
-        for (int u = 0; u < 4; u++) v[u] = ld_stream_u4(src + i + u * stride);
+            for (int u = 0; u < HB_FIX_UNROLL; u++) v[u] = ld_stream_256(in + 32 * (i + u * stride));
 #pragma unroll
-        for (int u = 0; u < 4; u++)
-            st_stream_u4(dst + i + u * stride, make_uint4(tr(v[u].x), tr(v[u].y), tr(v[u].z), tr(v[u].w)));
-    }
-    for (; i < n_vec; i += stride) {
-        const uint4 v = ld_stream_u4(src + i);
-        st_stream_u4(dst + i, make_uint4(tr(v.x), tr(v.y), tr(v.z), tr(v.w)));
+            for (int u = 0; u < HB_FIX_UNROLL; u++) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[u].v[k] = tr(v[u].v[k]);
+                st_stream_256(out + 32 * (i + u * stride), v[u]);
+            }
+        }
+        for (; i < n_vec; i += stride) {
+            u32x8 v = ld_stream_256(in + 32 * i);
+#pragma unroll
+            for (int k = 0; k < 8; k++) v.v[k] = tr(v.v[k]);
+            st_stream_256(out + 32 * i, v);
+        }
+        done = n_vec * 32;
+    } else
+#endif
+    {
+        const size_t n_vec = n / 16;
+        const uint4 *src = reinterpret_cast<const uint4 *>(in);
+        uint4 *dst = reinterpret_cast<uint4 *>(out);
+        for (; i + (HB_FIX_UNROLL - 1) * stride < n_vec; i += HB_FIX_UNROLL * stride) {
+            uint4 v[HB_FIX_UNROLL];
+#pragma unroll
+            for (int u = 0; u < HB_FIX_UNROLL; u++) v[u] = ld_stream_u4(src + i + u * stride);
+#pragma unroll
+            for (int u = 0; u < HB_FIX_UNROLL; u++)
+                st_stream_u4(dst + i + u * stride, make_uint4(tr(v[u].x), tr(v[u].y), tr(v[u].z), tr(v[u].w)));
+        }
+        for (; i < n_vec; i += stride) {
+            const uint4 v = ld_stream_u4(src + i);
+            st_stream_u4(dst + i, make_uint4(tr(v.x), tr(v.y), tr(v.z), tr(v.w)));
+        }
+        done = n_vec * 16;
     }
     if (blockIdx.x == 0) {
-        const size_t at = n_vec * 16 + threadIdx.x;
+        const size_t at = done + threadIdx.x;                  // < 32 leftover bytes
         if (at < n) out[at] = static_cast<uint8_t>(my[static_cast<uint32_t>(in[at]) << 5]);
     }
 }

@@ -101,9 +101,9 @@ hist_regions_kernel(const uint8_t *__restrict__ data, size_t n, size_t region_by
     const size_t begin = static_cast<size_t>(region) * region_bytes;
     if (begin < n) {
         const size_t end = min(n, begin + region_bytes);
+        const size_t stride = static_cast<size_t>(ctas_per_region) * kHistThreads;
         const size_t n_vec = (end - begin) / 16;
         const uint4 *vec = reinterpret_cast<const uint4 *>(data + begin);
-        const size_t stride = static_cast<size_t>(ctas_per_region) * kHistThreads;
         size_t i = static_cast<size_t>(part) * kHistThreads + threadIdx.x;
         for (; i + (kHistUnroll - 1) * stride < n_vec; i += kHistUnroll * stride) {
             uint4 v[kHistUnroll];

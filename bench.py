@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- BASELINE.json's metric: compress + decompress GB/s of input, and fraction of the HBM roofline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload uniform|zipf|english]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload uniform|zipf|english|zipf15|zipf20]
                     [--size BYTES]
 
 One "step" = one pass of the hot path over one batch of synthetic input resident in HBM:
@@ -138,7 +138,8 @@ class ClockSampler:
 # ---------------------------------------------------------------- workloads
 def make_workload(name: str, n: int, offset: int, device):
     from huff_encoding_b200 import datagen as G
-    gen = {"uniform": G.uniform, "zipf": G.zipf, "english": G.english}[name]
+    gen = {"uniform": G.uniform, "zipf": G.zipf, "english": G.english,
+           "zipf15": lambda *a, **k: G.zipf(*a, s=(15, 10), **k), "zipf20": lambda *a, **k: G.zipf(*a, s=(20, 10), **k)}[name]
     return gen(n, offset=offset, device=device)
 
 
@@ -433,7 +434,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="uniform", choices=["uniform", "zipf", "english"])
+    ap.add_argument("--workload", default="uniform", choices=["uniform", "zipf", "english", "zipf15", "zipf20"])
     ap.add_argument("--size", type=int, default=1 << 30, help="bytes per GPU")
     ap.add_argument("--no-general", action="store_true", help="skip the secondary general-path (zipf) measurement")
     args = ap.parse_args()

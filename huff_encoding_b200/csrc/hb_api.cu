@@ -308,6 +308,7 @@ void build_dec_tables(const hb_tree *tree, hb::DecTables *t, int cnt_bits) {
     const uint32_t root = tree->root;
     t->root = root;
     const int K = hb::kLutBits;
+    int n_slots = 0;
     for (uint32_t p = 0; p < (1u << K); p++) {
         if (leaf(root)) {
             // comp.rs:496,506-509: a lone root emits its letter for every bit
@@ -322,9 +323,29 @@ void build_dec_tables(const hb_tree *tree, hb::DecTables *t, int cnt_bits) {
             node = bit ? tree->nodes[node].right : tree->nodes[node].left;
             used++;
         }
-        // short code: len | letter << 8 ; long code: bit 7, node index in bits 8-15 (low) and 4-6 (high), len field 0
-        t->lut[p] = leaf(node) ? static_cast<uint16_t>(static_cast<uint32_t>(used) | (static_cast<uint32_t>(tree->nodes[node].letter) << 8))
-                               : static_cast<uint16_t>(0x80u | ((node & 0xFFu) << 8) | (((node >> 8) & 7u) << 4));
+        // short code: len | letter << 8 ; long code: bit 7 + the second-level slot of the depth-12 node in bits 8-15
+        if (leaf(node)) {
+            t->lut[p] = static_cast<uint16_t>(static_cast<uint32_t>(used) | (static_cast<uint32_t>(tree->nodes[node].letter) << 8));
+        } else {
+            int slot = -1;
+            for (int k = 0; k < n_slots; k++) if (t->slot_node[k] == node) { slot = k; break; }
+            if (slot < 0) {
+                slot = n_slots++;                          // at most 255 internal nodes exist, so slots never run out
+                t->slot_node[slot] = static_cast<uint16_t>(node);
+                for (uint32_t b8 = 0; b8 < 256; b8++) {    // stream bits 12..19 below this node
+                    uint32_t nd = node;
+                    int extra = 0;
+                    while (extra < 8 && !leaf(nd)) {
+                        nd = ((b8 >> (7 - extra)) & 1) ? tree->nodes[nd].right : tree->nodes[nd].left;
+                        extra++;
+                    }
+                    t->lut2[slot * 256 + b8] = leaf(nd)
+                        ? static_cast<uint16_t>(static_cast<uint32_t>(K + extra) | (static_cast<uint32_t>(tree->nodes[nd].letter) << 8))
+                        : static_cast<uint16_t>(0x80u | (static_cast<uint32_t>(slot) << 8));
+                }
+            }
+            t->lut[p] = static_cast<uint16_t>(0x80u | (static_cast<uint32_t>(slot) << 8));
+        }
     }
     // multi-letter count table over CB bits: greedy run of complete code words
     const int CB = cnt_bits;

@@ -64,12 +64,16 @@ constexpr int kScanGroup = 1024;                               // CTAs per offse
 constexpr int kGroup = 32;                                     // letters per 256-bit store in the write pass
 
 struct DecTables {                     // device resident, built on the host from the hb_tree
-    uint16_t lut[1 << kLutBits];       // bit7 = 0: len (bits 0-3) | letter << 8 ; bit7 = 1: long code, continue at node
-                                       // ((e >> 8) | ((e >> 4) & 7) << 8); its len field is 0
+    uint16_t lut[1 << kLutBits];       // bit7 = 0: len (bits 0-4) | letter << 8 ; bit7 = 1: code longer than 12 bits,
+                                       // slot (e >> 8) of the second level; its len field is 0
     uint8_t  cnt[1 << kCntBitsMax];    // indexed by the next cnt_bits bits: (bits consumed << 4) | letters completed,
                                        // 0 if not even one code fits
     uint32_t nodes[HB_MAX_NODES];      // left | right << 16 ; leaf: left = 0xFFFF, right = letter
     uint32_t root;
+    // second level (read from global memory / L1, only for codes of 13..20 bits): one 256-entry table per tree node
+    // at depth 12 ("slot"), indexed by stream bits 12..19: total len (bits 0-4) | letter << 8, or bit 7 if still longer
+    uint16_t slot_node[256];           // slot -> node index (to continue a bit-serial walk for codes > 20 bits)
+    uint16_t lut2[256 * 256];
 };
 
 struct DecParams {
@@ -105,8 +109,10 @@ __device__ __forceinline__ void stg256(void *p, const uint32_t (&v)[8]) {
                  :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 
-struct DecShared {                     // shared-space byte addresses
+struct DecShared {                     // shared-space byte addresses + the second-level table in global memory
     uint32_t win, lut, cnt, nodes;
+    const uint16_t *lut2;
+    const uint16_t *slot_node;
 };
 
 __device__ __forceinline__ uint32_t win_word_addr(uint32_t win, uint32_t i) { return win + ((i + (i >> 5)) << 2); }
@@ -141,9 +147,18 @@ struct BitReader {
 };
 
 __device__ __forceinline__ uint32_t lut_is_long(uint32_t e) { return e & 0x80u; }
-__device__ __forceinline__ uint32_t lut_len(uint32_t e) { return e & 0xFu; }
+__device__ __forceinline__ uint32_t lut_len(uint32_t e) { return e & 0x1Fu; }
 __device__ __forceinline__ uint32_t lut_letter(uint32_t e) { return e >> 8; }
-__device__ __forceinline__ uint32_t lut_node(uint32_t e) { return (e >> 8) | (((e >> 4) & 7u) << 8); }
+__device__ __forceinline__ uint32_t lut_slot(uint32_t e) { return e >> 8; }
+// Second-level lookup for a first-level entry with the long flag: stream bits 12..19 after the reader's position.
+// Returns an entry of the same layout (len 13..20 | letter << 8), or one with the long flag still set (> 20 bits).
+__device__ __forceinline__ uint32_t lut_resolve(const DecShared &s, uint32_t e, const BitReader &rd) {
+#ifdef HB_NO_LUT2                      // A/B switch: every code longer than 12 bits takes the bit-serial walk
+    return e;
+#endif
+    const uint32_t x = __funnelshift_l(rd.w1, rd.w0, rd.s);
+    return __ldg(s.lut2 + (lut_slot(e) << 8) + ((x >> (32 - kLutBits - 8)) & 0xFFu));
+}
 
 // Decode one code word starting at window bit q (table + tree walk, any length).  Returns its length, 0 if it would
 // end after q_avail.
@@ -156,7 +171,7 @@ __device__ __noinline__ uint32_t dec_one_slow(DecShared s, uint32_t q, uint32_t 
         len = lut_len(e);
         letter = lut_letter(e);
     } else {
-        uint32_t node = lut_node(e);
+        uint32_t node = __ldg(s.slot_node + lut_slot(e));
         len = kLutBits;
         for (;;) {
             const uint32_t nd = lds32(s.nodes + (node << 2));
@@ -214,7 +229,15 @@ __device__ __forceinline__ uint32_t dec_run(DecShared s, uint32_t q, uint32_t q_
             if (c) {
                 rd.skip(s.win, c >> 4);
                 n += c & 15u;
-            } else {                                                     // first code longer than CB bits
+                continue;
+            }
+            // first code longer than CB bits: second-level table (<= 20 bits), else bit-serial walk
+            uint32_t e = lds16(s.lut + (rd.peek() << 1));
+            if (lut_is_long(e)) e = lut_resolve(s, e, rd);
+            if (!lut_is_long(e)) {
+                rd.skip(s.win, lut_len(e));
+                n++;
+            } else {
                 uint32_t letter;
                 const uint32_t len = dec_one_slow(s, rd.q, q_avail, letter);
                 if (!len) { count = n; return kEnd32; }
@@ -223,7 +246,8 @@ __device__ __forceinline__ uint32_t dec_run(DecShared s, uint32_t q, uint32_t q_
             }
         }
         while (rd.q < q_stop) {                                          // last few letters: one per lookup
-            const uint32_t e = lds16(s.lut + (rd.peek() << 1));
+            uint32_t e = lds16(s.lut + (rd.peek() << 1));
+            if (lut_is_long(e)) e = lut_resolve(s, e, rd);
             if (!lut_is_long(e)) {
                 rd.skip(s.win, lut_len(e));
                 n++;
@@ -412,8 +436,10 @@ struct DecCarve {
     uint32_t *win; uint16_t *lut; uint8_t *cnt; uint32_t *nodes; uint32_t *exit; uint32_t *red;
     DecShared sh;
 };
-__device__ __forceinline__ DecCarve dec_carve(uint8_t *base) {
+__device__ __forceinline__ DecCarve dec_carve(uint8_t *base, const DecTables *tables) {
     DecCarve c;
+    c.sh.lut2 = tables->lut2;
+    c.sh.slot_node = tables->slot_node;
     c.win = reinterpret_cast<uint32_t *>(base);
     c.lut = reinterpret_cast<uint16_t *>(base + kDecOffLut);
     c.nodes = reinterpret_cast<uint32_t *>(base + kDecOffNodes);
@@ -430,7 +456,7 @@ __device__ __forceinline__ DecCarve dec_carve(uint8_t *base) {
 template <int CB>
 __global__ void __launch_bounds__(kDecThreads)
 dec_count_kernel(DecParams p, const DecTables *__restrict__ tables) {
-    DecCarve c = dec_carve(dec_smem);
+    DecCarve c = dec_carve(dec_smem, tables);
     dec_load_tables(tables, c.lut, c.cnt, c.nodes, CB);
     for (uint32_t blk = blockIdx.x; blk < p.n_blocks; blk += gridDim.x)
         dec_count_block<CB>(p, blk, 0, false, c.win, c.sh, c.exit, c.red);
@@ -450,7 +476,7 @@ __global__ void dec_verify_kernel(DecParams p, uint32_t *dirty, uint32_t *n_dirt
 template <int CB>
 __global__ void __launch_bounds__(kDecThreads)
 dec_fix_kernel(DecParams p, const DecTables *__restrict__ tables, uint32_t *dirty) {
-    DecCarve c = dec_carve(dec_smem);
+    DecCarve c = dec_carve(dec_smem, tables);
     __shared__ uint32_t s_next;
     dec_load_tables(tables, c.lut, c.cnt, c.nodes, CB);
     uint32_t cur = 1;
@@ -576,10 +602,48 @@ __device__ __noinline__ uint32_t slow_next(LetterSource &src) {
     return letter;
 }
 
+// 32 letters from the register bit window, one table lookup each, static byte inserts, one 256-bit store.
+// kResolve = false: branch-free body for trees without codes longer than the first-level table (the CTA-uniform
+// common case).  kResolve = true: a first-level miss is resolved per letter in the second-level table (13..20 bits).
+// Returns false with nothing stored and `reader` untouched when a code is longer than the tables cover; the caller
+// then redoes the group letter by letter.
+template <bool kResolve>
+__device__ __forceinline__ bool dec_fast_group(const DecShared &sh, BitReader &reader, uint8_t *dst) {
+    BitReader rd = reader;
+    uint32_t v[8];
+    uint32_t escape = 0;
+#pragma unroll
+    for (int j = 0; j < kGroup; j++) {
+        uint32_t e = lds16(sh.lut + (rd.peek() << 1));
+        if (kResolve) {
+            if (lut_is_long(e)) e = lut_resolve(sh, e, rd);               // rare, divergent
+        }
+        escape |= e;
+        // consume (the stream position rd.q is recomputed after the group)
+        rd.s += lut_len(e);
+        if (rd.s >= 32) {
+            rd.s -= 32;
+            rd.w0 = rd.w1;
+            rd.w1 = lds32(win_word_addr(sh.win, rd.wi));
+            rd.wi++;
+        }
+        // the letter sits in byte 1 of e: one PRMT drops it into byte j%4 of the output word
+        if ((j & 3) == 0) v[j >> 2] = __byte_perm(e, 0u, 0x4441);
+        else if ((j & 3) == 1) v[j >> 2] = __byte_perm(v[j >> 2], e, 0x3250);
+        else if ((j & 3) == 2) v[j >> 2] = __byte_perm(v[j >> 2], e, 0x3510);
+        else v[j >> 2] = __byte_perm(v[j >> 2], e, 0x5210);
+    }
+    if (lut_is_long(escape)) return false;
+    rd.q = ((rd.wi - 2) << 5) + rd.s;
+    stg256(dst, v);
+    reader = rd;
+    return true;
+}
+
 __global__ void __launch_bounds__(kDecThreads)
 dec_write_kernel(DecParams p, const DecTables *__restrict__ tables, const uint32_t *__restrict__ blk_local,
                  const uint64_t *__restrict__ group_off, uint8_t *__restrict__ out, uint64_t total_letters) {
-    DecCarve c = dec_carve(dec_smem);
+    DecCarve c = dec_carve(dec_smem, tables);
     __shared__ uint32_t s_w[kDecThreads / 32];
     dec_load_tables(tables, c.lut, nullptr, c.nodes);
     const int t = threadIdx.x;
@@ -587,6 +651,7 @@ dec_write_kernel(DecParams p, const DecTables *__restrict__ tables, const uint32
     // between two safety checks a thread reads at most one group of letters (+ refill look-ahead)
     const uint32_t reach = (kGroup + 1) * min(p.max_len, 255u) + 96;
     const uint32_t q_safe_group = kWinBits > reach ? kWinBits - reach : 0;
+    const bool has_long = p.max_len > kLutBits;                  // CTA-uniform: codes beyond the first-level table exist
 
     for (uint32_t blk = blockIdx.x; blk < p.n_blocks; blk += gridDim.x) {
         __syncthreads();
@@ -629,7 +694,8 @@ dec_write_kernel(DecParams p, const DecTables *__restrict__ tables, const uint32
         if (pos < lo && src.rd.q < q_safe_group) {                            // letters my predecessor writes (< 32)
             BitReader rd = src.rd;
             while (pos < lo) {
-                const uint32_t e = lds16(c.sh.lut + (rd.peek() << 1));
+                uint32_t e = lds16(c.sh.lut + (rd.peek() << 1));
+                if (lut_is_long(e)) e = lut_resolve(c.sh, e, rd);
                 if (lut_is_long(e)) break;
                 rd.skip(c.sh.win, lut_len(e));
                 pos++;
@@ -641,37 +707,8 @@ dec_write_kernel(DecParams p, const DecTables *__restrict__ tables, const uint32
             out[pos] = static_cast<uint8_t>(slow_next(src));
         while (pos + kGroup <= hi) {
             bool done = false;
-            if (!src.global_mode && src.rd.q < q_safe_group) {
-                // fast path: 32 letters, branch-free body, static byte inserts; redone letter by letter in the
-                // (rare) case that one of them has a code longer than the 12-bit table
-                BitReader rd = src.rd;
-                uint32_t v[8];
-                uint32_t escape = 0;
-#pragma unroll
-                for (int j = 0; j < kGroup; j++) {
-                    const uint32_t e = lds16(c.sh.lut + (rd.peek() << 1));
-                    escape |= e;
-                    // consume (the stream position rd.q is recomputed after the group)
-                    rd.s += lut_len(e);
-                    if (rd.s >= 32) {
-                        rd.s -= 32;
-                        rd.w0 = rd.w1;
-                        rd.w1 = lds32(win_word_addr(c.sh.win, rd.wi));
-                        rd.wi++;
-                    }
-                    // the letter sits in byte 1 of e: one PRMT drops it into byte j%4 of the output word
-                    if ((j & 3) == 0) v[j >> 2] = __byte_perm(e, 0u, 0x4441);
-                    else if ((j & 3) == 1) v[j >> 2] = __byte_perm(v[j >> 2], e, 0x3250);
-                    else if ((j & 3) == 2) v[j >> 2] = __byte_perm(v[j >> 2], e, 0x3510);
-                    else v[j >> 2] = __byte_perm(v[j >> 2], e, 0x5210);
-                }
-                rd.q = ((rd.wi - 2) << 5) + rd.s;
-                if (!lut_is_long(escape)) {
-                    stg256(out + pos, v);
-                    src.rd = rd;
-                    done = true;
-                }
-            }
+            if (!src.global_mode && src.rd.q < q_safe_group)
+                done = has_long ? dec_fast_group<true>(c.sh, src.rd, out + pos) : dec_fast_group<false>(c.sh, src.rd, out + pos);
             if (!done)
                 for (int j = 0; j < kGroup; j++) out[pos + j] = static_cast<uint8_t>(slow_next(src));
             pos += kGroup;

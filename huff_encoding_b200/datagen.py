@@ -71,9 +71,9 @@ def zipf_table(s_num: int = 12, s_den: int = 10) -> tuple[np.ndarray, np.ndarray
     k = np.arange(1, 257, dtype=np.float64)
     p = k ** (-(s_num / s_den))
     w = np.maximum(1, np.round(p / p.sum() * (1 << 32))).astype(np.uint64)
-    cum = np.cumsum(w)
-    thr = (cum * np.uint64(1 << 32)) // np.uint64(cum[-1])
-    return np.arange(256, dtype=np.uint8), thr.astype(np.uint64)
+    cum = [int(c) for c in np.cumsum(w)]                      # exact integers: cum * 2^32 can exceed 64 bits
+    thr = np.array([(c << 32) // cum[-1] for c in cum], dtype=np.uint64)
+    return np.arange(256, dtype=np.uint8), thr
 
 
 def _sample_np(n: int, seed: int, offset: int, sym: np.ndarray, thr: np.ndarray) -> np.ndarray:
@@ -112,8 +112,10 @@ def english(n: int, seed: int = SEED_BASE + 0, offset: int = 0, device=None):
     return _sample_np(n, seed, offset, sym, thr) if device is None else _sample_torch(n, seed, offset, sym, thr, device)
 
 
-def zipf(n: int, seed: int = SEED_BASE + 2, offset: int = 0, device=None):
-    sym, thr = zipf_table()
+def zipf(n: int, seed: int = SEED_BASE + 2, offset: int = 0, device=None, s: tuple[int, int] = (12, 10)):
+    """Zipf letters with exponent s[0]/s[1] (default 1.2 = BASELINE.json configs[2]; 1.5 and 2.0 give long-tailed
+    code sets whose rare letters get 13..16-bit codes)."""
+    sym, thr = zipf_table(*s)
     return _sample_np(n, seed, offset, sym, thr) if device is None else _sample_torch(n, seed, offset, sym, thr, device)
 
 

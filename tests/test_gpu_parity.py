@@ -170,6 +170,24 @@ def test_lengths_with_common_factor(hb):
     assert cd.huff_tree().raw.len_gcd == 2
 
 
+@pytest.mark.parametrize("s", [(15, 10), (20, 10)])
+def test_zipf_long_tail_codes_of_13_to_16_bits(hb, s):
+    # codes longer than the 12-bit first-level table are frequent enough that every decoder thread meets them
+    data = G.zipf((6 << 20) + 11, seed=77, s=s)
+    cd = _assert_compress_parity(hb, data)
+    assert 12 < cd.huff_tree().raw.max_len <= 20
+
+
+def test_geometric_tail_codes_in_all_three_decoder_levels(hb):
+    # P(k) ~ 0.75^k over 64 letters: code lengths 2..~26, so the first-level table, the second-level table (13..20
+    # bits) and the bit-serial walk (> 20 bits) are all hit, the first two often
+    rng = np.random.default_rng(21)
+    p = 0.75 ** np.arange(64)
+    data = rng.choice(np.arange(64, dtype=np.uint8) * 3 + 5, size=5_000_003, p=p / p.sum())
+    cd = _assert_compress_parity(hb, data)
+    assert cd.huff_tree().raw.max_len > 20
+
+
 def test_fibonacci_wide_codes(hb):
     # 36 Fibonacci-weighted letters: longest code 35 bits (> 32 -> wide encoder path), N = F(38)-1 ~ 39 M letters
     fib = [1, 1]

@@ -312,7 +312,7 @@ void build_dec_tables(const hb_tree *tree, hb::DecTables *t, int cnt_bits) {
     for (uint32_t p = 0; p < (1u << K); p++) {
         if (leaf(root)) {
             // comp.rs:496,506-509: a lone root emits its letter for every bit
-            t->lut[p] = static_cast<uint16_t>(1u | (static_cast<uint32_t>(tree->nodes[root].letter) << 8));
+            t->lut[p] = static_cast<uint16_t>((1u << hb::kLutLenShift) | tree->nodes[root].letter);
             continue;
         }
         // first code word
@@ -323,9 +323,9 @@ void build_dec_tables(const hb_tree *tree, hb::DecTables *t, int cnt_bits) {
             node = bit ? tree->nodes[node].right : tree->nodes[node].left;
             used++;
         }
-        // short code: len | letter << 8 ; long code: bit 7 + the second-level slot of the depth-12 node in bits 8-15
+        // short code: letter | len << 11 ; long code: long flag + the second-level slot of the depth-12 node
         if (leaf(node)) {
-            t->lut[p] = static_cast<uint16_t>(static_cast<uint32_t>(used) | (static_cast<uint32_t>(tree->nodes[node].letter) << 8));
+            t->lut[p] = static_cast<uint16_t>((static_cast<uint32_t>(used) << hb::kLutLenShift) | tree->nodes[node].letter);
         } else {
             int slot = -1;
             for (int k = 0; k < n_slots; k++) if (t->slot_node[k] == node) { slot = k; break; }
@@ -340,11 +340,11 @@ void build_dec_tables(const hb_tree *tree, hb::DecTables *t, int cnt_bits) {
                         extra++;
                     }
                     t->lut2[slot * 256 + b8] = leaf(nd)
-                        ? static_cast<uint16_t>(static_cast<uint32_t>(K + extra) | (static_cast<uint32_t>(tree->nodes[nd].letter) << 8))
-                        : static_cast<uint16_t>(0x80u | (static_cast<uint32_t>(slot) << 8));
+                        ? static_cast<uint16_t>((static_cast<uint32_t>(K + extra) << hb::kLutLenShift) | tree->nodes[nd].letter)
+                        : static_cast<uint16_t>(hb::kLutLongFlag | static_cast<uint32_t>(slot));
                 }
             }
-            t->lut[p] = static_cast<uint16_t>(0x80u | (static_cast<uint32_t>(slot) << 8));
+            t->lut[p] = static_cast<uint16_t>(hb::kLutLongFlag | static_cast<uint32_t>(slot));
         }
     }
     // multi-letter count table over CB bits: greedy run of complete code words

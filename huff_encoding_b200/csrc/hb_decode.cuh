@@ -64,14 +64,13 @@ constexpr int kScanGroup = 1024;                               // CTAs per offse
 constexpr int kGroup = 32;                                     // letters per 256-bit store in the write pass
 
 struct DecTables {                     // device resident, built on the host from the hb_tree
-    uint16_t lut[1 << kLutBits];       // bit7 = 0: len (bits 0-4) | letter << 8 ; bit7 = 1: code longer than 12 bits,
-                                       // slot (e >> 8) of the second level; its len field is 0
+    uint16_t lut[1 << kLutBits];       // letter | len << 11, or (code longer than 12 bits) slot | 0x100 with len 0
     uint8_t  cnt[1 << kCntBitsMax];    // indexed by the next cnt_bits bits: (bits consumed << 4) | letters completed,
                                        // 0 if not even one code fits
     uint32_t nodes[HB_MAX_NODES];      // left | right << 16 ; leaf: left = 0xFFFF, right = letter
     uint32_t root;
     // second level (read from global memory / L1, only for codes of 13..20 bits): one 256-entry table per tree node
-    // at depth 12 ("slot"), indexed by stream bits 12..19: total len (bits 0-4) | letter << 8, or bit 7 if still longer
+    // at depth 12 ("slot"), indexed by stream bits 12..19: letter | total len << 11, or slot | 0x100 if still longer
     uint16_t slot_node[256];           // slot -> node index (to continue a bit-serial walk for codes > 20 bits)
     uint16_t lut2[256 * 256];
 };
@@ -133,6 +132,13 @@ struct BitReader {
         wi += 2;
     }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(w1, w0, s) >> (32 - kLutBits); }
+    // byte offset of the first-level entry for the next kLutBits bits (mask + one LEA.HI with the table base)
+    // (the AND is opaque to the optimiser, which would otherwise turn it back into shift + mask + add)
+    __device__ __forceinline__ uint32_t peek_lut_off() const {
+        uint32_t y;
+        asm("and.b32 %0, %1, %2;" : "=r"(y) : "r"(__funnelshift_l(w1, w0, s)), "n"(~((1u << (32 - kLutBits)) - 1u)));
+        return y >> (31 - kLutBits);
+    }
     __device__ __forceinline__ uint32_t peek_bits(uint32_t k) const { return __funnelshift_l(w1, w0, s) >> (32 - k); }
     __device__ __forceinline__ void skip(uint32_t win, uint32_t l) {  // l < 32
         s += l;
@@ -146,10 +152,15 @@ struct BitReader {
     }
 };
 
-__device__ __forceinline__ uint32_t lut_is_long(uint32_t e) { return e & 0x80u; }
-__device__ __forceinline__ uint32_t lut_len(uint32_t e) { return e & 0x1Fu; }
-__device__ __forceinline__ uint32_t lut_letter(uint32_t e) { return e >> 8; }
-__device__ __forceinline__ uint32_t lut_slot(uint32_t e) { return e >> 8; }
+// Table entry (both levels), 16 bits: letter (bits 0-7) | long flag (bit 8) | code length (bits 11-15).  The length in
+// the top bits makes "position += length" one shift-add (LEA.HI) with no mask; a long entry has length 0 and carries
+// the second-level slot in the letter field.
+constexpr uint32_t kLutLongFlag = 0x100u;
+constexpr int kLutLenShift = 11;
+__device__ __forceinline__ uint32_t lut_is_long(uint32_t e) { return e & kLutLongFlag; }
+__device__ __forceinline__ uint32_t lut_len(uint32_t e) { return e >> kLutLenShift; }
+__device__ __forceinline__ uint32_t lut_letter(uint32_t e) { return e & 0xFFu; }
+__device__ __forceinline__ uint32_t lut_slot(uint32_t e) { return e & 0xFFu; }
 // Second-level lookup for a first-level entry with the long flag: stream bits 12..19 after the reader's position.
 // Returns an entry of the same layout (len 13..20 | letter << 8), or one with the long flag still set (> 20 bits).
 __device__ __forceinline__ uint32_t lut_resolve(const DecShared &s, uint32_t e, const BitReader &rd) {
@@ -186,82 +197,79 @@ __device__ __noinline__ uint32_t dec_one_slow(DecShared s, uint32_t q, uint32_t 
 
 // Advance from q over whole code words while q < q_stop; count them.  Returns the first code-word start >= q_stop,
 // or kEnd32 when a code word does not fit below q_avail.
+//
+// The common-case loop keeps only (w0, w1, position, next word): the funnel shift takes the position modulo 32 by
+// itself and a refill is due exactly when bit 5 of the position flips (a step is < 32 bits).  Every step adds
+// bits << 4 | letters to ONE accumulator; the letter count falls out at the end as acc - 16 * (bits consumed).
 template <int CB>
 __device__ __forceinline__ uint32_t dec_run(DecShared s, uint32_t q, uint32_t q_stop, uint32_t q_avail, uint32_t &count) {
-    uint32_t n = 0;
     if (q == kEnd32) { count = 0; return kEnd32; }
     if (q < q_stop && q_stop + 2 * CB <= q_avail) {
         // common case (everything but the very end of the stream): no code word can run past q_avail here
-        BitReader rd;
-        rd.init(s.win, q);
-        // several multi-letter steps per trip: one position check per trip, straight-line code between the lookups
+        const uint32_t q_begin = q;
+        uint32_t wi = q >> 5;
+        uint32_t w0 = lds32(win_word_addr(s.win, wi));
+        uint32_t w1 = lds32(win_word_addr(s.win, wi + 1));
+        wi += 2;
+        uint32_t acc = 0;
+        auto step = [&](uint32_t bits) {                                 // bits < 32
+            const uint32_t qn = q + bits;
+            if ((qn ^ q) & 32u) {
+                w0 = w1;
+                w1 = lds32(win_word_addr(s.win, wi));
+                wi++;
+            }
+            q = qn;
+        };
+        auto peek = [&]() { return __funnelshift_l(w1, w0, q); };
+        // two multi-letter steps per trip: one position check per trip, straight-line code between the lookups
         // (measured: 2 steps per trip = 21 % faster than 1)
-#if HB_COUNT_UNROLL == 4
-        while (rd.q + 4 * CB <= q_stop) {
-            const uint32_t c1 = lds8(s.cnt + rd.peek_bits(CB));
-            if (!c1) break;
-            rd.skip(s.win, c1 >> 4);
-            const uint32_t c2 = lds8(s.cnt + rd.peek_bits(CB));
-            if (!c2) { n += c1 & 15u; break; }
-            rd.skip(s.win, c2 >> 4);
-            const uint32_t c3 = lds8(s.cnt + rd.peek_bits(CB));
-            if (!c3) { n += (c1 & 15u) + (c2 & 15u); break; }
-            rd.skip(s.win, c3 >> 4);
-            const uint32_t c4 = lds8(s.cnt + rd.peek_bits(CB));
-            if (!c4) { n += (c1 & 15u) + (c2 & 15u) + (c3 & 15u); break; }
-            rd.skip(s.win, c4 >> 4);
-            n += (c1 & 15u) + (c2 & 15u) + (c3 & 15u) + (c4 & 15u);
-        }
-#endif
-#if HB_COUNT_UNROLL >= 2
-        while (rd.q + 2 * CB <= q_stop) {
-            const uint32_t c1 = lds8(s.cnt + rd.peek_bits(CB));
-            if (!c1) break;
-            rd.skip(s.win, c1 >> 4);
-            const uint32_t c2 = lds8(s.cnt + rd.peek_bits(CB));
-            if (!c2) { n += c1 & 15u; break; }
-            rd.skip(s.win, c2 >> 4);
-            n += (c1 & 15u) + (c2 & 15u);
-        }
-#endif
-        while (rd.q + CB <= q_stop) {                                    // multi-letter steps: all inside [q, q_stop)
-            const uint32_t c = lds8(s.cnt + rd.peek_bits(CB));
-            if (c) {
-                rd.skip(s.win, c >> 4);
-                n += c & 15u;
-                continue;
+        if (q_stop >= 2 * CB) {
+            const uint32_t q_lim2 = q_stop - 2 * CB;
+            while (q <= q_lim2) {
+                const uint32_t c1 = lds8(s.cnt + (peek() >> (32 - CB)));
+                if (!c1) break;
+                step(c1 >> 4);
+                const uint32_t c2 = lds8(s.cnt + (peek() >> (32 - CB)));
+                if (!c2) { acc += c1; break; }
+                step(c2 >> 4);
+                acc += c1 + c2;
             }
-            // first code longer than CB bits: second-level table (<= 20 bits), else bit-serial walk
-            uint32_t e = lds16(s.lut + (rd.peek() << 1));
-            if (lut_is_long(e)) e = lut_resolve(s, e, rd);
-            if (!lut_is_long(e)) {
-                rd.skip(s.win, lut_len(e));
-                n++;
-            } else {
+        }
+        for (;;) {
+            const bool multi = q + CB <= q_stop;                         // a multi-letter step stays inside [q, q_stop)
+            if (!multi && q >= q_stop) break;
+            if (multi) {
+                const uint32_t c = lds8(s.cnt + (peek() >> (32 - CB)));
+                if (c) { step(c >> 4); acc += c; continue; }
+            }
+            // one letter: the last few before q_stop, or a code longer than CB bits (second-level table up to 20
+            // bits, else the bit-serial walk)
+            uint32_t y;
+            asm("and.b32 %0, %1, %2;" : "=r"(y) : "r"(peek()), "n"(~((1u << (32 - kLutBits)) - 1u)));
+            uint32_t e = lds16(s.lut + (y >> (31 - kLutBits)));
+            if (lut_is_long(e))
+                e = __ldg(s.lut2 + (lut_slot(e) << 8) + ((peek() >> (32 - kLutBits - 8)) & 0xFFu));
+            uint32_t len = lut_len(e);
+            if (lut_is_long(e)) {
                 uint32_t letter;
-                const uint32_t len = dec_one_slow(s, rd.q, q_avail, letter);
-                if (!len) { count = n; return kEnd32; }
-                n++;
-                rd.init(s.win, rd.q + len);
-            }
-        }
-        while (rd.q < q_stop) {                                          // last few letters: one per lookup
-            uint32_t e = lds16(s.lut + (rd.peek() << 1));
-            if (lut_is_long(e)) e = lut_resolve(s, e, rd);
-            if (!lut_is_long(e)) {
-                rd.skip(s.win, lut_len(e));
-                n++;
+                len = dec_one_slow(s, q, q_avail, letter);
+                if (!len) { count = acc - ((q - q_begin) << 4); return kEnd32; }
+                acc += (len << 4) + 1;
+                q += len;                                                // any length: reload the two words
+                wi = q >> 5;
+                w0 = lds32(win_word_addr(s.win, wi));
+                w1 = lds32(win_word_addr(s.win, wi + 1));
+                wi += 2;
             } else {
-                uint32_t letter;
-                const uint32_t len = dec_one_slow(s, rd.q, q_avail, letter);
-                if (!len) { count = n; return kEnd32; }
-                n++;
-                rd.init(s.win, rd.q + len);
+                step(len);
+                acc += (len << 4) + 1;
             }
         }
-        count = n;
-        return rd.q;
+        count = acc - ((q - q_begin) << 4);
+        return q;
     }
+    uint32_t n = 0;
     while (q < q_stop) {                                                 // end of the stream: every step checked
         uint32_t letter;
         const uint32_t len = dec_one_slow(s, q, q_avail, letter);
@@ -446,10 +454,14 @@ __device__ __forceinline__ DecCarve dec_carve(uint8_t *base, const DecTables *ta
     c.red = reinterpret_cast<uint32_t *>(base + kDecOffRed);
     c.cnt = base + kDecOffCnt;
     c.exit = reinterpret_cast<uint32_t *>(base + kDecOffExit);
-    c.sh.win = smem_addr(c.win);
-    c.sh.lut = smem_addr(c.lut);
-    c.sh.cnt = smem_addr(c.cnt);
-    c.sh.nodes = smem_addr(c.nodes);
+    // one opaque base register: otherwise the compiler rematerialises the shared-window base (S2UR + ULEA + IMAD)
+    // inside the decode loops instead of keeping it live
+    uint32_t b = smem_addr(base);
+    asm volatile("mov.u32 %0, %0;" : "+r"(b));
+    c.sh.win = b;
+    c.sh.lut = b + static_cast<uint32_t>(kDecOffLut);
+    c.sh.cnt = b + static_cast<uint32_t>(kDecOffCnt);
+    c.sh.nodes = b + static_cast<uint32_t>(kDecOffNodes);
     return c;
 }
 
@@ -614,7 +626,7 @@ __device__ __forceinline__ bool dec_fast_group(const DecShared &sh, BitReader &r
     uint32_t escape = 0;
 #pragma unroll
     for (int j = 0; j < kGroup; j++) {
-        uint32_t e = lds16(sh.lut + (rd.peek() << 1));
+        uint32_t e = lds16(sh.lut + rd.peek_lut_off());
         if (kResolve) {
             if (lut_is_long(e)) e = lut_resolve(sh, e, rd);               // rare, divergent
         }
@@ -627,11 +639,11 @@ __device__ __forceinline__ bool dec_fast_group(const DecShared &sh, BitReader &r
             rd.w1 = lds32(win_word_addr(sh.win, rd.wi));
             rd.wi++;
         }
-        // the letter sits in byte 1 of e: one PRMT drops it into byte j%4 of the output word
-        if ((j & 3) == 0) v[j >> 2] = __byte_perm(e, 0u, 0x4441);
-        else if ((j & 3) == 1) v[j >> 2] = __byte_perm(v[j >> 2], e, 0x3250);
-        else if ((j & 3) == 2) v[j >> 2] = __byte_perm(v[j >> 2], e, 0x3510);
-        else v[j >> 2] = __byte_perm(v[j >> 2], e, 0x5210);
+        // the letter sits in byte 0 of e: one PRMT drops it into byte j%4 of the output word
+        if ((j & 3) == 0) v[j >> 2] = __byte_perm(e, 0u, 0x4440);
+        else if ((j & 3) == 1) v[j >> 2] = __byte_perm(v[j >> 2], e, 0x3240);
+        else if ((j & 3) == 2) v[j >> 2] = __byte_perm(v[j >> 2], e, 0x3410);
+        else v[j >> 2] = __byte_perm(v[j >> 2], e, 0x4210);
     }
     if (lut_is_long(escape)) return false;
     rd.q = ((rd.wi - 2) << 5) + rd.s;
@@ -694,7 +706,7 @@ dec_write_kernel(DecParams p, const DecTables *__restrict__ tables, const uint32
         if (pos < lo && src.rd.q < q_safe_group) {                            // letters my predecessor writes (< 32)
             BitReader rd = src.rd;
             while (pos < lo) {
-                uint32_t e = lds16(c.sh.lut + (rd.peek() << 1));
+                uint32_t e = lds16(c.sh.lut + rd.peek_lut_off());
                 if (lut_is_long(e)) e = lut_resolve(c.sh, e, rd);
                 if (lut_is_long(e)) break;
                 rd.skip(c.sh.win, lut_len(e));

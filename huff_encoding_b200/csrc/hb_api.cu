@@ -217,9 +217,9 @@ hb_status upload_enc_table(hb_ctx *ctx, const hb_tree *tree) {
         if (!tree->has_code[b]) continue;
         const uint32_t len = tree->code_len[b];
         if (len > HB_MAX_ENCODE_BITS) continue;            // such letters are rejected per input (check_encodable)
-        const uint64_t code = tree->code[b];
-        t.lo[b] = make_uint2(static_cast<uint32_t>(code & 0xFFFFFFFFull), len);
-        t.hi[b] = static_cast<uint32_t>(code >> 32);
+        const uint64_t left = len ? tree->code[b] << (64 - len) : 0;       // code left-aligned in 64 bits
+        t.lo[b] = make_uint2(static_cast<uint32_t>(left >> 32), len);
+        t.hi[b] = static_cast<uint32_t>(left);
         max_len = std::max(max_len, len);
     }
     HB_CUDA(cudaMemcpyAsync(ctx->d_enc_table, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream));

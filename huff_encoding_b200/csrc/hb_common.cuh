@@ -20,6 +20,22 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
     asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
     return r;
 }
+// 32-bit shared-space address of a pointer into shared memory
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+struct u32x8 { uint32_t v[8]; };
+__device__ __forceinline__ u32x8 ld_stream_256(const void *p) {
+    u32x8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_256(void *p, const u32x8 &r) {
+    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
+                 : "memory");
+}
+
 __device__ __forceinline__ void st_stream_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }

@@ -93,7 +93,6 @@ struct DecParams {
 };
 
 // ---------------------------------------------------------------- shared-space access (32-bit addresses in registers)
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
     uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v;
 }

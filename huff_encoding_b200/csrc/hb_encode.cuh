@@ -7,13 +7,14 @@
 //     inter-CTA communication at all (no look-back descriptors, no cooperative launch, nothing to wait on);
 //   * inside a region the 32 warps of the CTA take 32 consecutive TILES per round; one __syncthreads per round
 //     exchanges the 32 tile bit totals through shared memory and every warp derives its 64-bit global bit offset;
-//   * a tile is 32 lanes x 8 rounds of CHUNKS; a chunk is S consecutive letters (S = 4 when every code has <= 16
-//     bits, 2 for <= 32 bits, 1 for <= 64 bits) merged into one <= 64-bit value.  Lane i takes chunk r*32 + i in
-//     round r, so the 32 lanes read 32*S consecutive bytes (coalesced) and write adjacent stream words;
-//   * codes come from a lane-replicated shared-memory table: entry (b, lane) lives at [b*32 + lane] as (code, len),
-//     so the 32 lookups of a warp never conflict whatever the data;
-//   * a warp scan of the chunk lengths (two rounds packed per 32-bit scan) gives every chunk its bit offset inside the
-//     tile; chunks are OR-ed into a per-warp shared-memory staging stream (<= 3 shared atomics per chunk);
+//   * a tile is 32 lanes x 32 (S = 4; else 16) CONSECUTIVE letters: one 256-bit load per lane (a warp reads 1 KiB), and
+//     a lane's codes are contiguous in the stream, so ONE warp scan per tile (of the lanes' bit totals) places them;
+//   * codes come from a lane-replicated shared-memory table: entry (b, lane) lives at [b*32 + lane] as (code
+//     left-aligned in 32 bits, len), so the 32 lookups of a warp never conflict whatever the data;
+//   * every lane streams its codes through a 64-bit register packer in PIECES of <= 32 bits (S = 4: all codes
+//     <= 16 bits, a piece is two letters; S = 2: codes <= 32 bits, one letter; S = 1: codes <= 64 bits, a letter is
+//     two pieces) and ORs each completed 32-bit word into the per-warp shared-memory staging stream: one shared
+//     atomic per 32 stream bits (the words two lanes share need the OR; the others take it as a plain store);
 //   * the staging stream is laid out at (global offset % 32), so its words ARE the global stream words and go out as
 //     coalesced big-endian 32-bit stores.  The word two tiles share is written once, by the later tile, which
 //     re-derives the last 32 bits of its predecessor from the predecessor's last 32 letters (every code has >= 1
@@ -28,19 +29,34 @@ namespace hb {
 
 constexpr int kEncWarps = 32;
 constexpr int kEncThreads = kEncWarps * 32;
-constexpr int kEncRounds = 8;                                   // chunks per lane per tile
-constexpr int kEncStageWords = 32 * kEncRounds * 2 + 8;         // 256 chunks x 64 bits, + tail slot + slack
+constexpr int kEncRoundLetters = 32768;                         // region sizes are multiples of this (whole rounds)
 
-constexpr int kEncRoundLetters = kEncWarps * 32 * kEncRounds * 4;   // region sizes are multiples of this (S = 4 round)
+// consecutive letters per lane: 32 (one 256-bit load) when a piece is two letters, else 16; 16 pieces either way
+__host__ __device__ constexpr int enc_lane_letters(int S) { return S == 4 ? 32 : 16; }
+__host__ __device__ constexpr int enc_tile_letters(int S) { return 32 * enc_lane_letters(S); }   // one warp
+__host__ __device__ constexpr int enc_max_bits(int S) { return S == 4 ? 16 : (S == 2 ? 32 : 64); }
+__host__ __device__ constexpr int enc_stage_words(int S) { return enc_tile_letters(S) * enc_max_bits(S) / 32 + 4; }   // + shared first word + slack
+static_assert(kEncRoundLetters % (kEncWarps * enc_tile_letters(4)) == 0 && kEncRoundLetters % (kEncWarps * enc_tile_letters(1)) == 0,
+              "regions must hold whole rounds");
 
-// device-resident code table
+// device-resident code table: codes LEFT-aligned
 struct EncTable {
-    uint2 lo[256];        // (low <= 32 code bits, len) -- for len <= 32 this is the whole code
-    uint32_t hi[256];     // code bits above 32 (len > 32 only)
+    uint2 lo[256];        // (first min(len, 32) code bits, left-aligned in 32 bits; len)
+    uint32_t hi[256];     // the remaining len - 32 bits, left-aligned (len > 32 only)
 };
 
+// S == 4 (the hot variant) pins the lane-replicated table at the ABSOLUTE shared address 0x10000: entry (b, lane)
+// is then at 0x10000 | b << 8 | lane << 3, which ONE byte-permute builds from the raw input word (no shift, mask,
+// add).  The shared memory below 0x10000 (minus the static variables) is left unused; the staging follows the table.
+constexpr uint32_t kEncTabAbs = 0x10000u;
 constexpr size_t enc_smem_bytes(int S) {
-    return 256 * 32 * sizeof(uint2) + (S == 1 ? 256 * sizeof(uint32_t) : 0) + kEncWarps * kEncStageWords * sizeof(uint32_t);
+    return (S == 4 ? static_cast<size_t>(kEncTabAbs) : 0) + 256 * 32 * sizeof(uint2) + (S == 1 ? 256 * sizeof(uint32_t) : 0) +
+           static_cast<size_t>(kEncWarps) * enc_stage_words(S) * sizeof(uint32_t);
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t a) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a));
+    return r;
 }
 
 // exact bit count of a region from its histogram: sum_b hist[b] * len[b]  (block-wide, all threads get the result)
@@ -59,23 +75,79 @@ __device__ __forceinline__ unsigned long long enc_region_base(const uint32_t *__
     return total;
 }
 
-template <int S> struct EncLoad;
-template <> struct EncLoad<4> { using type = uint32_t; };
-template <> struct EncLoad<2> { using type = uint16_t; };
-template <> struct EncLoad<1> { using type = uint8_t; };
-
 extern __shared__ __align__(16) uint8_t enc_smem[];
+
+// 64-bit register bit packer of one lane.  `hi` holds the `fill` (< 32) pending bits left-aligned; a piece of L <= 32
+// bits (left-aligned in `pl`, zeros below) is appended and a completed word is OR-ed into the staging stream.
+struct EncPacker {
+    uint32_t *ptr;
+    uint32_t hi, fill;
+    __device__ __forceinline__ void append(uint32_t pl, uint32_t L) {
+        hi |= pl >> fill;
+        const uint32_t lo = __funnelshift_r(0u, pl, fill);        // the bits of pl that fall past the pending word
+        fill += L;
+        if (fill >= 32) {
+            atomicOr(ptr, hi);
+            ptr++;
+            hi = lo;
+            fill -= 32;
+        }
+    }
+    // a piece of L <= 64 bits, left-aligned in (ph:pl): up to two completed words; the second one lies entirely
+    // inside this piece, so it is a plain store
+    __device__ __forceinline__ void append64(uint32_t ph, uint32_t pl, uint32_t L) {
+        const uint32_t w0 = hi | (ph >> fill);
+        const uint32_t w1 = __funnelshift_r(pl, ph, fill);
+        const uint32_t w2 = __funnelshift_r(0u, pl, fill);
+        const uint32_t nf = fill + L;
+        // straight-line: two predicated stores, two selects (lanes differ in how many words they complete)
+        if (nf >= 32) atomicOr(ptr, w0);
+        if (nf >= 64) ptr[1] = w1;
+        hi = nf >= 64 ? w2 : (nf >= 32 ? w1 : w0);
+        ptr += nf >> 5;
+        fill = nf & 31;
+    }
+    __device__ __forceinline__ void finish() { if (fill) atomicOr(ptr, hi); }
+};
+
+// The one cut-short tile at the end of the input (n % tile != 0): letter by letter, no register arrays.
+template <int S>
+__device__ __noinline__ uint32_t enc_partial_bits(const uint8_t *__restrict__ data, size_t lane_base, uint32_t n_mine,
+                                                  const uint2 *my_tab) {
+    uint32_t bits = 0;
+    for (uint32_t j = 0; j < n_mine; j++) bits += my_tab[static_cast<uint32_t>(data[lane_base + j]) << 5].y;
+    return bits;
+}
+template <int S>
+__device__ __noinline__ void enc_partial_append(const uint8_t *__restrict__ data, size_t lane_base, uint32_t n_mine,
+                                                const uint2 *my_tab, const uint32_t *s_hi, uint32_t *ptr, uint32_t fill) {
+    EncPacker pk;
+    pk.ptr = ptr;
+    pk.fill = fill;
+    pk.hi = 0;
+    for (uint32_t j = 0; j < n_mine; j++) {
+        const uint32_t b = data[lane_base + j];
+        const uint2 e = my_tab[b << 5];
+        pk.append(e.x, min(e.y, 32u));
+        if (S == 1 && e.y > 32) pk.append(s_hi[b], e.y - 32);
+    }
+    pk.finish();
+}
 
 template <int S>
 __global__ void __launch_bounds__(kEncThreads, 1)
 encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable *__restrict__ table,
                       uint32_t start_bit, uint32_t *__restrict__ out32, const uint32_t *__restrict__ region_hist,
                       size_t region_letters, unsigned long long *__restrict__ total_bits_out) {
-    constexpr int kTile = 32 * kEncRounds * S;                  // letters per tile: 1024 / 512 / 256
-    using load_t = typename EncLoad<S>::type;
+    constexpr int kLane = enc_lane_letters(S);
+    constexpr int kTile = enc_tile_letters(S);
+    constexpr int kPieces = 16;                                  // register-held pieces per lane
+    constexpr int kStageWords = enc_stage_words(S);
 
-    uint2 *s_tab = reinterpret_cast<uint2 *>(enc_smem);                                     // [256][32]
-    uint32_t *s_hi = reinterpret_cast<uint32_t *>(enc_smem + 256 * 32 * sizeof(uint2));    // [256] (S == 1)
+    // S == 4: the table sits at absolute shared address kEncTabAbs (see enc_smem_bytes)
+    uint8_t *tab_bytes = enc_smem + (S == 4 ? kEncTabAbs - smem_addr(enc_smem) : 0u);
+    uint2 *s_tab = reinterpret_cast<uint2 *>(tab_bytes);                                    // [256][32]
+    uint32_t *s_hi = reinterpret_cast<uint32_t *>(tab_bytes + 256 * 32 * sizeof(uint2));    // [256] (S == 1)
     uint32_t *s_stage_all = s_hi + (S == 1 ? 256 : 0);
     __shared__ unsigned long long s_red[kEncWarps];
     __shared__ uint32_t s_tile_bits[2][kEncWarps];
@@ -91,7 +163,8 @@ encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable
     // global bit offset of this region: everything the regions before it emit (+ the caller's start bit)
     unsigned long long running = start_bit + enc_region_base(region_hist, blockIdx.x, s_tab, s_red);
 
-    uint32_t *stage = s_stage_all + warp * kEncStageWords;      // word m = global stream word (tile offset / 32) + m
+    uint32_t *stage = s_stage_all + warp * kStageWords;         // word m = global stream word (tile offset / 32) + m
+    const bool aligned32 = (reinterpret_cast<uintptr_t>(data) & 31) == 0;
     const uint2 *my_tab = s_tab + lane;
     const uint32_t n_rounds = static_cast<uint32_t>((region_end - region_begin + kEncWarps * kTile - 1) / (kEncWarps * kTile));
 
@@ -99,77 +172,71 @@ encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable
         const size_t tile_base = region_begin + (static_cast<size_t>(round) * kEncWarps + warp) * kTile;
         const bool live = tile_base < region_end;               // region_end == n whenever a tile is cut short
         const bool full = tile_base + kTile <= n;
+        const size_t lane_base = tile_base + static_cast<size_t>(lane) * kLane;
 
-        // ---- load this lane's 8 chunks (round r: chunk r*32 + lane) and merge each chunk's codes
-        unsigned long long val[kEncRounds];
-        uint32_t len[kEncRounds];
-        {
-            load_t raw[kEncRounds];
-            const load_t *src = reinterpret_cast<const load_t *>(data + tile_base);
-            if (full) {
+        // next round's letters: start them on their way into L2 now (all warps of a CTA load right after the barrier)
+        if (lane_base + static_cast<size_t>(kEncWarps) * kTile < n)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(data + lane_base + static_cast<size_t>(kEncWarps) * kTile));
+
+        // ---- pass 1: this lane's consecutive letters, table lookups; the pieces and their lengths (one byte each)
+        //      stay in registers.  The single cut-short tile of the input takes the letter-by-letter path.
+        uint32_t raw[kLane / 4];
+        uint32_t pv[kPieces];
+        uint32_t plen[S == 4 ? 8 : kPieces / 4];                // S == 4: one length per quad; else a byte per piece
+        uint32_t lane_bits = 0;
+        const uint32_t n_mine = full ? kLane
+                                     : (lane_base >= n ? 0u : static_cast<uint32_t>(min(static_cast<size_t>(kLane), n - lane_base)));
+        if (full) {
+            if (kLane == 32 && aligned32) {
+                const u32x8 v = ld_stream_256(data + lane_base);
 #pragma unroll
-                for (int r = 0; r < kEncRounds; r++) raw[r] = src[r * 32 + lane];
+                for (int j = 0; j < 8; j++) raw[j] = v.v[j];
             } else {
 #pragma unroll
-                for (int r = 0; r < kEncRounds; r++) {
-                    uint32_t v = 0;
-                    const size_t at = tile_base + static_cast<size_t>(r * 32 + lane) * S;
-#pragma unroll
-                    for (int k = 0; k < S; k++)
-                        if (at + k < n) v |= static_cast<uint32_t>(data[at + k]) << (8 * k);
-                    raw[r] = static_cast<load_t>(v);
+                for (int h = 0; h < kLane / 16; h++) {
+                    const uint4 v = ld_stream_u4(reinterpret_cast<const uint4 *>(data + lane_base) + h);
+                    raw[4 * h + 0] = v.x; raw[4 * h + 1] = v.y; raw[4 * h + 2] = v.z; raw[4 * h + 3] = v.w;
                 }
             }
+            if (S == 4) {
+                // quads: four letters -> one <= 64-bit piece (qh:ql, left-aligned) and its length
+                const uint32_t lane_addr = kEncTabAbs + (static_cast<uint32_t>(lane) << 3);
 #pragma unroll
-            for (int r = 0; r < kEncRounds; r++) {
-                const size_t at = tile_base + static_cast<size_t>(r * 32 + lane) * S;
-                if (S == 4) {
-                    const uint32_t w = raw[r];
-                    uint2 e0 = my_tab[(w & 0xFFu) << 5], e1 = my_tab[((w >> 8) & 0xFFu) << 5];
-                    uint2 e2 = my_tab[((w >> 16) & 0xFFu) << 5], e3 = my_tab[(w >> 24) << 5];
-                    if (!full) {
-                        if (at + 0 >= n) e0 = make_uint2(0, 0);
-                        if (at + 1 >= n) e1 = make_uint2(0, 0);
-                        if (at + 2 >= n) e2 = make_uint2(0, 0);
-                        if (at + 3 >= n) e3 = make_uint2(0, 0);
-                    }
-                    const uint32_t v01 = (e0.x << e1.y) | e1.x, l01 = e0.y + e1.y;   // <= 32 bits
-                    const uint32_t v23 = (e2.x << e3.y) | e3.x, l23 = e2.y + e3.y;
-                    val[r] = (static_cast<unsigned long long>(v01) << l23) | v23;
-                    len[r] = l01 + l23;
-                } else if (S == 2) {
-                    const uint32_t w = raw[r];
-                    uint2 e0 = my_tab[(w & 0xFFu) << 5], e1 = my_tab[((w >> 8) & 0xFFu) << 5];
-                    if (!full) {
-                        if (at + 0 >= n) e0 = make_uint2(0, 0);
-                        if (at + 1 >= n) e1 = make_uint2(0, 0);
-                    }
-                    val[r] = (static_cast<unsigned long long>(e0.x) << e1.y) | e1.x;
-                    len[r] = e0.y + e1.y;
-                } else {
-                    const uint32_t b = raw[r];
-                    uint2 e0 = my_tab[b << 5];
-                    uint32_t h = s_hi[b];
-                    if (!full && at >= n) { e0 = make_uint2(0, 0); h = 0; }
-                    val[r] = (static_cast<unsigned long long>(h) << 32) | e0.x;
-                    len[r] = e0.y;
+                for (int q = 0; q < 8; q++) {
+                    const uint32_t w = raw[q];
+                    const uint2 e0 = lds_u2(__byte_perm(w, lane_addr, 0x7604));     // 0x10000 | byte << 8 | lane << 3
+                    const uint2 e1 = lds_u2(__byte_perm(w, lane_addr, 0x7614));
+                    const uint2 e2 = lds_u2(__byte_perm(w, lane_addr, 0x7624));
+                    const uint2 e3 = lds_u2(__byte_perm(w, lane_addr, 0x7634));
+                    const uint32_t v01 = e0.x | (e1.x >> e0.y), l01 = e0.y + e1.y;  // codes <= 16 bits
+                    const uint32_t v23 = e2.x | (e3.x >> e2.y), l23 = e2.y + e3.y;
+                    pv[2 * q] = v01 | __funnelshift_rc(v23, 0u, l01);
+                    pv[2 * q + 1] = __funnelshift_rc(0u, v23, l01);
+                    plen[q] = l01 + l23;
+                    lane_bits += l01 + l23;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kPieces / 4; k++) plen[k] = 0;
+#pragma unroll
+                for (int k = 0; k < kPieces; k++) {
+                    const uint32_t b = (raw[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+                    const uint2 e = my_tab[b << 5];
+                    pv[k] = e.x;
+                    plen[k >> 2] |= e.y << (8 * (k & 3));      // S == 1: up to 64, the second piece comes from s_hi
+                    lane_bits += e.y;
                 }
             }
+        } else if (live) {
+            lane_bits = enc_partial_bits<S>(data, lane_base, n_mine, my_tab);
         }
 
-        // ---- bit offsets: warp scans, two rounds per 32-bit word (a round totals at most 32 * 64 bits)
-        uint32_t off[kEncRounds];
-        uint32_t tile_bits = 0;
-#pragma unroll
-        for (int r = 0; r < kEncRounds; r += 2) {
-            const uint32_t packed = len[r] | (len[r + 1] << 16);
-            const uint32_t incl = warp_incl_scan(packed);
-            const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            const uint32_t excl = incl - packed;
-            off[r] = tile_bits + (excl & 0xFFFFu);
-            tile_bits += tot & 0xFFFFu;
-            off[r + 1] = tile_bits + (excl >> 16);
-            tile_bits += tot >> 16;
+        // ---- bit offsets: ONE warp scan per tile (a lane totals at most 1024 bits)
+        uint32_t tile_bits, off;
+        {
+            const uint32_t incl = warp_incl_scan(lane_bits);
+            tile_bits = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            off = incl - lane_bits;
         }
 
         // ---- one barrier per round: exchange the 32 tile totals, derive this tile's global bit offset
@@ -200,28 +267,51 @@ encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable
                 if (lane + d < 32) after += o;
             }
             after -= e.y;
-            const uint32_t piece = after < 32 ? (e.x << after) : 0u;   // low code bits that land in the last 32 bits
+            // the low 32 bits of my code, right-aligned
+            uint32_t low;
+            if (S == 1 && e.y > 32)
+                low = static_cast<uint32_t>(((static_cast<unsigned long long>(e.x) << 32) | s_hi[b]) >> (64 - e.y));
+            else
+                low = e.y ? e.x >> (32 - e.y) : 0u;
+            const uint32_t piece = after < 32 ? (low << after) : 0u;     // the part that lands in the last 32 bits
             pred_tail = __reduce_or_sync(0xFFFFFFFFu, piece);
         }
 
-        // ---- OR the chunks into the zeroed staging stream, already shifted by (global offset % 32): staging word m
-        //      is global word W0 + m, whose first rr bits are the predecessor's last rr bits
+        // ---- OR the lanes' bit strings into the zeroed staging stream, already shifted by (global offset % 32):
+        //      staging word m is global word W0 + m, whose first rr bits are the predecessor's last rr bits
         const uint32_t rr = static_cast<uint32_t>(excl & 31);
-        const uint32_t n_local_words = (rr + tile_bits + 31) / 32 + 3;
-        for (uint32_t i = lane; i < n_local_words; i += 32) stage[i] = 0;
+        const uint32_t n_local_vecs = ((rr + tile_bits + 31) / 32 + 3 + 3) / 4;           // <= kStageWords / 4
+        for (uint32_t i = lane; i < n_local_vecs; i += 32) reinterpret_cast<uint4 *>(stage)[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
-        if (lane == 0 && rr) atomicOr(&stage[0], pred_tail << (32 - rr));   // OR: other lanes' chunks share word 0
+        if (lane == 0 && rr) atomicOr(&stage[0], pred_tail << (32 - rr));   // OR: other lanes' bits share word 0
+        if (full) {
+            const uint32_t at = off + rr;
+            EncPacker pk;
+            pk.ptr = stage + (at >> 5);
+            pk.fill = at & 31;
+            pk.hi = 0;
+            if (S == 4) {
 #pragma unroll
-        for (int r = 0; r < kEncRounds; r++) {
-            const uint32_t L = len[r];
-            if (L == 0) continue;                               // only tail tiles / letters without a code
-            const unsigned long long top = val[r] << (64 - L);  // left-aligned chunk
-            const uint32_t hi = static_cast<uint32_t>(top >> 32), lo = static_cast<uint32_t>(top);
-            const uint32_t at = off[r] + rr;
-            const uint32_t w = at >> 5, s = at & 31;
-            atomicOr(&stage[w], hi >> s);
-            if (s + L > 32) atomicOr(&stage[w + 1], __funnelshift_r(lo, hi, s));
-            if (s + L > 64) atomicOr(&stage[w + 2], __funnelshift_r(0u, lo, s));
+                for (int q = 0; q < 8; q++) pk.append64(pv[2 * q], pv[2 * q + 1], plen[q]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < kPieces; k++) {
+                    const uint32_t l = (plen[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+                    if (S == 1) {
+                        pk.append(pv[k], min(l, 32u));
+                        if (l > 32) {                            // rare: the code's remaining bits
+                            const uint32_t b = (raw[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+                            pk.append(s_hi[b], l - 32);
+                        }
+                    } else {
+                        pk.append(pv[k], l);
+                    }
+                }
+            }
+            pk.finish();
+        } else {
+            const uint32_t at = off + rr;
+            enc_partial_append<S>(data, lane_base, n_mine, my_tab, s_hi, stage + (at >> 5), at & 31);
         }
         const bool is_last_tile = tile_base + kTile >= n;
         if (lane == 0 && is_last_tile && total_bits_out) *total_bits_out = excl + tile_bits - start_bit;

@@ -19,20 +19,6 @@ constexpr int kFixThreads = 512;
 #define HB_FIX_UNROLL 4
 #endif
 
-struct u32x8 { uint32_t v[8]; };
-__device__ __forceinline__ u32x8 ld_stream_256(const void *p) {
-    u32x8 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
-                 : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void st_stream_256(void *p, const u32x8 &r) {
-    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 :: "l"(p), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
-                 : "memory");
-}
-
 // L == 8: out[i] = table[in[i]] for n bytes; table lane-replicated in shared memory ([256][32] u32, conflict-free).
 // in / out 32-byte aligned -> 256-bit loads and stores (one full sector per lane); else 128-bit.
 __global__ void __launch_bounds__(kFixThreads)

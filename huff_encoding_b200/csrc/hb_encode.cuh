@@ -168,36 +168,50 @@ encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable
     const uint2 *my_tab = s_tab + lane;
     const uint32_t n_rounds = static_cast<uint32_t>((region_end - region_begin + kEncWarps * kTile - 1) / (kEncWarps * kTile));
 
+    // this lane's letters of a full tile: one 256-bit load (or 128-bit loads)
+    uint32_t raw[kLane / 4];
+    auto load_raw = [&](size_t at) {
+        if (kLane == 32 && aligned32) {
+            const u32x8 v = ld_stream_256(data + at);
+#pragma unroll
+            for (int j = 0; j < 8; j++) raw[j] = v.v[j];
+        } else {
+#pragma unroll
+            for (int h = 0; h < kLane / 16; h++) {
+                const uint4 v = ld_stream_u4(reinterpret_cast<const uint4 *>(data + at) + h);
+                raw[4 * h + 0] = v.x; raw[4 * h + 1] = v.y; raw[4 * h + 2] = v.z; raw[4 * h + 3] = v.w;
+            }
+        }
+    };
+    // S == 4 software-pipelines the loads: the registers of `raw` are refilled for the NEXT round as soon as this
+    // round's lookups are done, so the load latency hides behind the scan, the barrier and the packing
+    constexpr bool kPipelined = S == 4;
+    if (kPipelined) {
+        const size_t first = region_begin + static_cast<size_t>(warp) * kTile;
+        if (first + kTile <= n && first < region_end) load_raw(first + static_cast<size_t>(lane) * kLane);
+    }
+
     for (uint32_t round = 0; round < n_rounds; round++) {
         const size_t tile_base = region_begin + (static_cast<size_t>(round) * kEncWarps + warp) * kTile;
         const bool live = tile_base < region_end;               // region_end == n whenever a tile is cut short
         const bool full = tile_base + kTile <= n;
         const size_t lane_base = tile_base + static_cast<size_t>(lane) * kLane;
 
-        // next round's letters: start them on their way into L2 now (all warps of a CTA load right after the barrier)
-        if (lane_base + static_cast<size_t>(kEncWarps) * kTile < n)
+        if (!kPipelined && lane_base + static_cast<size_t>(kEncWarps) * kTile < n)   // next round's letters -> L2
             asm volatile("prefetch.global.L2 [%0];" :: "l"(data + lane_base + static_cast<size_t>(kEncWarps) * kTile));
+
+        // one of the predecessor tile's last 32 letters (its tail bits are re-derived below): issued early
+        const uint32_t pred_letter = (live && tile_base > 0) ? data[tile_base - 32 + lane] : 0u;
 
         // ---- pass 1: this lane's consecutive letters, table lookups; the pieces and their lengths (one byte each)
         //      stay in registers.  The single cut-short tile of the input takes the letter-by-letter path.
-        uint32_t raw[kLane / 4];
         uint32_t pv[kPieces];
         uint32_t plen[S == 4 ? 8 : kPieces / 4];                // S == 4: one length per quad; else a byte per piece
         uint32_t lane_bits = 0;
         const uint32_t n_mine = full ? kLane
                                      : (lane_base >= n ? 0u : static_cast<uint32_t>(min(static_cast<size_t>(kLane), n - lane_base)));
         if (full) {
-            if (kLane == 32 && aligned32) {
-                const u32x8 v = ld_stream_256(data + lane_base);
-#pragma unroll
-                for (int j = 0; j < 8; j++) raw[j] = v.v[j];
-            } else {
-#pragma unroll
-                for (int h = 0; h < kLane / 16; h++) {
-                    const uint4 v = ld_stream_u4(reinterpret_cast<const uint4 *>(data + lane_base) + h);
-                    raw[4 * h + 0] = v.x; raw[4 * h + 1] = v.y; raw[4 * h + 2] = v.z; raw[4 * h + 3] = v.w;
-                }
-            }
+            if (!kPipelined) load_raw(lane_base);
             if (S == 4) {
                 // quads: four letters -> one <= 64-bit piece (qh:ql, left-aligned) and its length
                 const uint32_t lane_addr = kEncTabAbs + (static_cast<uint32_t>(lane) << 3);
@@ -215,6 +229,9 @@ encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable
                     plen[q] = l01 + l23;
                     lane_bits += l01 + l23;
                 }
+                // `raw` is free: next round's tile (same warp), if it is a full one of this region
+                const size_t next_base = tile_base + static_cast<size_t>(kEncWarps) * kTile;
+                if (next_base + kTile <= n && next_base < region_end) load_raw(next_base + static_cast<size_t>(lane) * kLane);
             } else {
 #pragma unroll
                 for (int k = 0; k < kPieces / 4; k++) plen[k] = 0;
@@ -239,7 +256,9 @@ encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable
             off = incl - lane_bits;
         }
 
-        // ---- one barrier per round: exchange the 32 tile totals, derive this tile's global bit offset
+        // ---- one barrier per round: exchange the 32 tile totals, derive this tile's global bit offset.  (A
+        //      barrier-free hand-over from tile to tile through shared-memory flags was measured 2x SLOWER: 32
+        //      dependent hops per round are longer than the round's work.)
         if (!live) tile_bits = 0;
         if (lane == 0) s_tile_bits[round & 1][warp] = tile_bits;
         __syncthreads();
@@ -257,7 +276,7 @@ encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable
         // ---- last 32 bits of the predecessor tile, recomputed from its last 32 letters
         uint32_t pred_tail = 0;
         if (tile_base > 0) {
-            const uint32_t b = data[tile_base - 32 + lane];
+            const uint32_t b = pred_letter;
             const uint2 e = my_tab[b << 5];
             // suffix sum of the lengths of the letters after mine
             uint32_t after = e.y;
@@ -281,7 +300,9 @@ encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable
         //      staging word m is global word W0 + m, whose first rr bits are the predecessor's last rr bits
         const uint32_t rr = static_cast<uint32_t>(excl & 31);
         const uint32_t n_local_vecs = ((rr + tile_bits + 31) / 32 + 3 + 3) / 4;           // <= kStageWords / 4
-        for (uint32_t i = lane; i < n_local_vecs; i += 32) reinterpret_cast<uint4 *>(stage)[i] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < (kStageWords / 4 + 31) / 32; k++)
+            if (lane + 32 * k < n_local_vecs) reinterpret_cast<uint4 *>(stage)[lane + 32 * k] = make_uint4(0, 0, 0, 0);
         __syncwarp();
         if (lane == 0 && rr) atomicOr(&stage[0], pred_tail << (32 - rr));   // OR: other lanes' bits share word 0
         if (full) {
@@ -323,7 +344,12 @@ encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable
         const unsigned long long end_bit = excl + tile_bits;
         const uint32_t n_full = static_cast<uint32_t>((end_bit >> 5) - w0);
         uint32_t *dst = out32 + w0;
-        for (uint32_t m = lane; m < n_full; m += 32) st_stream_u32(dst + m, bswap32(stage[m]));
+        {
+            const uint32_t *sp = stage + lane;
+            uint32_t *gp = dst + lane;
+#pragma unroll 1
+            for (uint32_t m = lane; m < n_full; m += 32, sp += 32, gp += 32) st_stream_u32(gp, bswap32(*sp));
+        }
         if (is_last_tile && (end_bit & 31) && lane == 0) {
             // the stream's final partial word: pad bits are zero (comp.rs:446-447), write only the bytes that exist
             const uint32_t word = stage[n_full];

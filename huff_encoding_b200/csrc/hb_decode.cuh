@@ -139,6 +139,15 @@ struct BitReader {
         return y >> (31 - kLutBits);
     }
     __device__ __forceinline__ uint32_t peek_bits(uint32_t k) const { return __funnelshift_l(w1, w0, s) >> (32 - k); }
+    __device__ __forceinline__ void consume(uint32_t win, uint32_t l) {  // l < 32; leaves q stale (see users)
+        s += l;
+        if (s >= 32) {
+            s -= 32;
+            w0 = w1;
+            w1 = lds32(win_word_addr(win, wi));
+            wi++;
+        }
+    }
     __device__ __forceinline__ void skip(uint32_t win, uint32_t l) {  // l < 32
         s += l;
         q += l;
@@ -703,14 +712,26 @@ dec_write_kernel(DecParams p, const DecTables *__restrict__ tables, const uint32
 
         uint64_t pos = first;
         if (pos < lo && src.rd.q < q_safe_group) {                            // letters my predecessor writes (< 32)
+            // the warp runs this loop for its slowest lane (~30 trips): 32-bit trip counter, no position tracking,
+            // and no long-code test at all when the tree has no code beyond the first-level table
             BitReader rd = src.rd;
-            while (pos < lo) {
-                uint32_t e = lds16(c.sh.lut + rd.peek_lut_off());
-                if (lut_is_long(e)) e = lut_resolve(c.sh, e, rd);
-                if (lut_is_long(e)) break;
-                rd.skip(c.sh.win, lut_len(e));
-                pos++;
+            uint32_t k = static_cast<uint32_t>(lo - pos);
+            if (!has_long) {
+#pragma unroll 1
+                for (; k; k--) rd.consume(c.sh.win, lut_len(lds16(c.sh.lut + rd.peek_lut_off())));
+            } else {
+#pragma unroll 1
+                for (; k; k--) {
+                    uint32_t e = lds16(c.sh.lut + rd.peek_lut_off());
+                    if (lut_is_long(e)) {
+                        e = lut_resolve(c.sh, e, rd);
+                        if (lut_is_long(e)) break;                            // > 20 bits: letter by letter below
+                    }
+                    rd.consume(c.sh.win, lut_len(e));
+                }
             }
+            rd.q = ((rd.wi - 2) << 5) + rd.s;
+            pos = lo - k;
             src.rd = rd;
         }
         for (; pos < lo; pos++) (void)slow_next(src);

@@ -109,7 +109,6 @@ struct hb_ctx {
     int dec_count_grid = 0, dec_write_grid = 0;
     bool spoil_speculation = false;      // HB_DEBUG_SPOIL_SPECULATION=1 (tests): force the cross-CTA repair path
     uint32_t last_repairs = 0;           // chunks repaired by dec_fix_kernel in the last count pass
-    int cnt_bits = 13;                   // HB_CNT_BITS=12|13|14: index width of the multi-letter count table (13 measured best)
     hb::DecParams last_dec;
     uint64_t last_dec_total = 0;
     bool last_dec_valid = false;
@@ -372,7 +371,7 @@ void build_dec_tables(const hb_tree *tree, hb::DecTables *t, int cnt_bits) {
 hb_status upload_dec_tables(hb_ctx *ctx, const hb_tree *tree) {
     if (ctx->dec_tree_valid && same_nodes(ctx->dec_tree_cached, *tree)) return HB_OK;
     static thread_local hb::DecTables t;
-    build_dec_tables(tree, &t, ctx->cnt_bits);
+    build_dec_tables(tree, &t, hb::kCntBits);
     HB_CUDA(cudaMemcpyAsync(ctx->d_dec_tables, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream));
     HB_CUDA(cudaStreamSynchronize(ctx->stream));       // `t` is reused by the next call
     ctx->dec_tree_cached = *tree;
@@ -457,7 +456,7 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
     p.len_gcd = tree->len_gcd ? tree->len_gcd : 1;
     p.fixed_len = (tree->min_len == tree->max_len) ? tree->max_len : 0;
     p.max_len = tree->max_len ? tree->max_len : 1;
-    p.cnt_bits = static_cast<uint32_t>(ctx->cnt_bits);
+    p.cnt_bits = static_cast<uint32_t>(hb::kCntBits);
     p.spoil_speculation = ctx->spoil_speculation ? 1u : 0u;
     ctx->last_repairs = 0;
     if (tree->nodes[tree->root].left == HB_NO_CHILD) { p.fixed_len = 1; p.len_gcd = 1; }
@@ -469,10 +468,12 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
     p.blk_count = ctx->blk_count.p;
 
     const int grid = static_cast<int>(std::min<uint64_t>(ctx->dec_count_grid, n_blocks));
-    const size_t smem_count = hb::dec_smem_count(ctx->cnt_bits);
-    if (ctx->cnt_bits == 14) hb::dec_count_kernel<14><<<grid, hb::kDecThreads, smem_count, ctx->stream>>>(p, ctx->d_dec_tables);
-    else if (ctx->cnt_bits == 13) hb::dec_count_kernel<13><<<grid, hb::kDecThreads, smem_count, ctx->stream>>>(p, ctx->d_dec_tables);
-    else hb::dec_count_kernel<12><<<grid, hb::kDecThreads, smem_count, ctx->stream>>>(p, ctx->d_dec_tables);
+    const size_t smem_count = hb::dec_smem_count(hb::kCntBits);
+    // trees without codes beyond the count table's index take the instance without the zero-entry tests
+    if (p.max_len > static_cast<uint32_t>(hb::kCntBits))
+        hb::dec_count_kernel<true><<<grid, hb::kDecThreads, smem_count, ctx->stream>>>(p, ctx->d_dec_tables);
+    else
+        hb::dec_count_kernel<false><<<grid, hb::kDecThreads, smem_count, ctx->stream>>>(p, ctx->d_dec_tables);
     ctx->launches++;
     HB_CUDA(cudaGetLastError());
 
@@ -491,9 +492,7 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
         ctx->last_repairs += ctx->h_dec_result->n_dirty;
         if (round == 1) { g_last_error = "decoder chain repair did not converge"; return HB_ERR_CUDA; }
         // rare: a chunk whose speculative entry was wrong even after a 1024-bit look-back -> serial repair
-        if (ctx->cnt_bits == 14) hb::dec_fix_kernel<14><<<1, hb::kDecThreads, smem_count, ctx->stream>>>(p, ctx->d_dec_tables, ctx->dirty.p);
-        else if (ctx->cnt_bits == 13) hb::dec_fix_kernel<13><<<1, hb::kDecThreads, smem_count, ctx->stream>>>(p, ctx->d_dec_tables, ctx->dirty.p);
-        else hb::dec_fix_kernel<12><<<1, hb::kDecThreads, smem_count, ctx->stream>>>(p, ctx->d_dec_tables, ctx->dirty.p);
+        hb::dec_fix_kernel<<<1, hb::kDecThreads, smem_count, ctx->stream>>>(p, ctx->d_dec_tables, ctx->dirty.p);
         ctx->launches++;
         HB_CUDA(cudaGetLastError());
     }
@@ -609,13 +608,9 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
         HB_CUDA(cudaMallocHost(&ctx->h_dec_result, sizeof(DecResult)));
         HB_CUDA(cudaMallocHost(&ctx->h_hist, 256 * sizeof(uint64_t)));
         HB_CUDA(cudaMallocHost(&ctx->h_total_bits, sizeof(unsigned long long)));
-        { const char *cb = std::getenv("HB_CNT_BITS"); if (cb) { int v = std::atoi(cb); if (v >= 12 && v <= 14) ctx->cnt_bits = v; } }
-        HB_CUDA(cudaFuncSetAttribute(hb::dec_count_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::dec_smem_count(12))));
-        HB_CUDA(cudaFuncSetAttribute(hb::dec_count_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::dec_smem_count(13))));
-        HB_CUDA(cudaFuncSetAttribute(hb::dec_count_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::dec_smem_count(14))));
-        HB_CUDA(cudaFuncSetAttribute(hb::dec_fix_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::dec_smem_count(12))));
-        HB_CUDA(cudaFuncSetAttribute(hb::dec_fix_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::dec_smem_count(13))));
-        HB_CUDA(cudaFuncSetAttribute(hb::dec_fix_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::dec_smem_count(14))));
+        HB_CUDA(cudaFuncSetAttribute(hb::dec_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::dec_smem_count(hb::kCntBits))));
+        HB_CUDA(cudaFuncSetAttribute(hb::dec_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::dec_smem_count(hb::kCntBits))));
+        HB_CUDA(cudaFuncSetAttribute(hb::dec_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::dec_smem_count(hb::kCntBits))));
         HB_CUDA(cudaFuncSetAttribute(hb::dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::kDecSmemWrite)));
         int occ = 0;
         HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::hist_lane_columns_kernel, hb::kHistThreads, 0));
@@ -626,9 +621,7 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
         HB_CUDA(cudaFuncSetAttribute(hb::encode_regions_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::enc_smem_bytes(4))));
         HB_CUDA(cudaFuncSetAttribute(hb::encode_regions_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::enc_smem_bytes(2))));
         HB_CUDA(cudaFuncSetAttribute(hb::encode_regions_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::enc_smem_bytes(1))));
-        if (ctx->cnt_bits == 14) HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::dec_count_kernel<14>, hb::kDecThreads, hb::dec_smem_count(14)));
-        else if (ctx->cnt_bits == 13) HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::dec_count_kernel<13>, hb::kDecThreads, hb::dec_smem_count(13)));
-        else HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::dec_count_kernel<12>, hb::kDecThreads, hb::dec_smem_count(12)));
+        HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::dec_count_kernel<true>, hb::kDecThreads, hb::dec_smem_count(hb::kCntBits)));
         ctx->dec_count_grid = ctx->sm_count * std::max(occ, 1);
         HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hb::dec_write_kernel, hb::kDecThreads, hb::kDecSmemWrite));
         ctx->dec_write_grid = ctx->sm_count * std::max(occ, 1);

@@ -55,7 +55,11 @@ constexpr int kWinWords = kHaloWords + kChunkWords + kHaloWords;
 constexpr int kWinPhys = kWinWords + (kWinWords >> 5) + 4;     // padded: phys(i) = i + i/32 (+ slack for look-ahead)
 constexpr uint32_t kWinBits = kWinWords * 32u;
 constexpr int kLutBits = 12;
-constexpr int kCntBitsMax = 14;                                 // the multi-letter count table may look at up to 14 bits
+#ifndef HB_CNT_BITS
+#define HB_CNT_BITS 13                                            // 12 and 14 measured slower
+#endif
+constexpr int kCntBits = HB_CNT_BITS;                           // index width of the multi-letter count table
+constexpr int kCntBitsMax = 14;
 constexpr uint32_t kEnd32 = 0xFFFFFFFFu;
 constexpr uint64_t kEnd64 = ~0ull;
 constexpr int kLookbackBits = HB_LOOKBACK_BITS;                             // in-CTA look-back window W (thread 0 uses the full halo);
@@ -204,13 +208,15 @@ __device__ __noinline__ uint32_t dec_one_slow(DecShared s, uint32_t q, uint32_t 
 }
 
 // Advance from q over whole code words while q < q_stop; count them.  Returns the first code-word start >= q_stop,
-// or kEnd32 when a code word does not fit below q_avail.
+// or kEnd32 when a code word does not fit below q_avail.  kLong = the tree has codes longer than the count table's
+// index (else every table entry completes at least one letter and the zero tests disappear).
 //
 // The common-case loop keeps only (w0, w1, position, next word): the funnel shift takes the position modulo 32 by
 // itself and a refill is due exactly when bit 5 of the position flips (a step is < 32 bits).  Every step adds
 // bits << 4 | letters to ONE accumulator; the letter count falls out at the end as acc - 16 * (bits consumed).
-template <int CB>
+template <bool kLong>
 __device__ __forceinline__ uint32_t dec_run(DecShared s, uint32_t q, uint32_t q_stop, uint32_t q_avail, uint32_t &count) {
+    constexpr int CB = kCntBits;
     if (q == kEnd32) { count = 0; return kEnd32; }
     if (q < q_stop && q_stop + 2 * CB <= q_avail) {
         // common case (everything but the very end of the stream): no code word can run past q_avail here
@@ -236,10 +242,10 @@ __device__ __forceinline__ uint32_t dec_run(DecShared s, uint32_t q, uint32_t q_
             const uint32_t q_lim2 = q_stop - 2 * CB;
             while (q <= q_lim2) {
                 const uint32_t c1 = lds8(s.cnt + (peek() >> (32 - CB)));
-                if (!c1) break;
+                if (kLong && !c1) break;                                 // kLong: some code is longer than CB bits
                 step(c1 >> 4);
                 const uint32_t c2 = lds8(s.cnt + (peek() >> (32 - CB)));
-                if (!c2) { acc += c1; break; }
+                if (kLong && !c2) { acc += c1; break; }
                 step(c2 >> 4);
                 acc += c1 + c2;
             }
@@ -249,7 +255,7 @@ __device__ __forceinline__ uint32_t dec_run(DecShared s, uint32_t q, uint32_t q_
             if (!multi && q >= q_stop) break;
             if (multi) {
                 const uint32_t c = lds8(s.cnt + (peek() >> (32 - CB)));
-                if (c) { step(c >> 4); acc += c; continue; }
+                if (!kLong || c) { step(c >> 4); acc += c; continue; }
             }
             // one letter: the last few before q_stop, or a code longer than CB bits (second-level table up to 20
             // bits, else the bit-serial walk)
@@ -348,7 +354,7 @@ __device__ __forceinline__ void dec_load_window(const DecParams &p, uint32_t chu
 }
 
 // The count pass for one chunk.
-template <int CB>
+template <bool kLong>
 __device__ void dec_count_block(const DecParams &p, uint32_t blk, uint64_t entry_override, bool use_override,
                                 uint32_t *win, DecShared s, uint32_t *s_exit, uint32_t *s_red) {
     const int t = threadIdx.x;
@@ -393,7 +399,7 @@ __device__ void dec_count_block(const DecParams &p, uint32_t blk, uint64_t entry
                 if (rem) q0 += p.len_gcd - rem;
             }
             uint32_t dummy;
-            entry = q0 >= q_lo ? q0 : dec_run<CB>(s, q0, q_lo, q_avail, dummy);
+            entry = q0 >= q_lo ? q0 : dec_run<kLong>(s, q0, q_lo, q_avail, dummy);
         }
     }
 
@@ -402,7 +408,7 @@ __device__ void dec_count_block(const DecParams &p, uint32_t blk, uint64_t entry
     bool redo = active;
     for (int round = 0;; round++) {
         if (round > kDecThreads + 1) asm volatile("trap;");   // cannot happen: thread t is final after t rounds
-        if (redo) exitq = dec_run<CB>(s, entry, q_hi, q_avail, count);
+        if (redo) exitq = dec_run<kLong>(s, entry, q_hi, q_avail, count);
         s_exit[t] = exitq;
         __syncthreads();
         redo = false;
@@ -473,13 +479,13 @@ __device__ __forceinline__ DecCarve dec_carve(uint8_t *base, const DecTables *ta
     return c;
 }
 
-template <int CB>
+template <bool kLong>
 __global__ void __launch_bounds__(kDecThreads)
 dec_count_kernel(DecParams p, const DecTables *__restrict__ tables) {
     DecCarve c = dec_carve(dec_smem, tables);
-    dec_load_tables(tables, c.lut, c.cnt, c.nodes, CB);
+    dec_load_tables(tables, c.lut, c.cnt, c.nodes, kCntBits);
     for (uint32_t blk = blockIdx.x; blk < p.n_blocks; blk += gridDim.x)
-        dec_count_block<CB>(p, blk, 0, false, c.win, c.sh, c.exit, c.red);
+        dec_count_block<kLong>(p, blk, 0, false, c.win, c.sh, c.exit, c.red);
 }
 
 // dirty[j] = 1 when CTA j's entry is not its predecessor's exit.  n_dirty accumulates.
@@ -493,12 +499,11 @@ __global__ void dec_verify_kernel(DecParams p, uint32_t *dirty, uint32_t *n_dirt
 }
 
 // Serial repair of mismatching CTAs (single CTA).  Each repaired chunk may change its exit and dirty its successor.
-template <int CB>
 __global__ void __launch_bounds__(kDecThreads)
 dec_fix_kernel(DecParams p, const DecTables *__restrict__ tables, uint32_t *dirty) {
     DecCarve c = dec_carve(dec_smem, tables);
     __shared__ uint32_t s_next;
-    dec_load_tables(tables, c.lut, c.cnt, c.nodes, CB);
+    dec_load_tables(tables, c.lut, c.cnt, c.nodes, kCntBits);
     uint32_t cur = 1;
     for (;;) {
         // find the next dirty chunk at or after cur
@@ -521,7 +526,7 @@ dec_fix_kernel(DecParams p, const DecTables *__restrict__ tables, uint32_t *dirt
         const uint64_t old_exit = vexit[j];
         const uint64_t entry = vexit[j - 1];
         __syncthreads();
-        dec_count_block<CB>(p, j, entry, true, c.win, c.sh, c.exit, c.red);
+        dec_count_block<true>(p, j, entry, true, c.win, c.sh, c.exit, c.red);
         if (threadIdx.x == 0) {
             dirty[j] = 0;
             if (j + 1 < p.n_blocks && vexit[j] != old_exit) dirty[j + 1] = 1;
@@ -637,8 +642,8 @@ __device__ __forceinline__ bool dec_fast_group(const DecShared &sh, BitReader &r
         uint32_t e = lds16(sh.lut + rd.peek_lut_off());
         if (kResolve) {
             if (lut_is_long(e)) e = lut_resolve(sh, e, rd);               // rare, divergent
+            escape |= e;                                                  // (no long entries exist when !kResolve)
         }
-        escape |= e;
         // consume (the stream position rd.q is recomputed after the group)
         rd.s += lut_len(e);
         if (rd.s >= 32) {

@@ -318,6 +318,27 @@ def test_device_api_matches_oracle_and_start_bit(eng):
         assert not bits[sb + ref_bits.size: (sb + ref_bits.size + 7) // 8 * 8].any()
 
 
+def test_device_input_pointer_alignment(eng):
+    # the encoder takes 256-bit loads when the letters are 32-byte aligned and 128-bit loads otherwise; the device API
+    # requires 16-byte alignment (include/huffb200.h) and says so instead of misreading
+    import torch
+    from huff_encoding_b200 import api
+    data = G.zipf((3 << 20) + 77, seed=5)
+    comp, pad_o, _ = O.compress(data)
+    big = torch.zeros(data.size + 256, dtype=torch.uint8, device=eng.device)
+    base = (-big.data_ptr()) % 32                      # first 32-byte aligned element
+    for off in (base, base + 16, base + 48):
+        view = big[off: off + data.size]
+        view.copy_(torch.from_numpy(data))
+        assert view.data_ptr() % 32 == (off - base) % 32
+        out, n, pad, tree = eng.compress(view)
+        assert n == comp.size and pad == pad_o
+        assert np.array_equal(out[:n].cpu().numpy(), comp)
+    view = big[base + 1: base + 1 + data.size]
+    with pytest.raises((api.HuffCudaError, ValueError, RuntimeError)):
+        eng.compress(view)
+
+
 def test_shard_decode_building_blocks(eng):
     import torch
     data = G.english(3_000_000)

@@ -20,26 +20,26 @@ namespace {
 // ---- std::collections::BinaryHeap, specialised to "smaller weight = greater in heap order"
 class BranchHeap {
 public:
-    explicit BranchHeap(const hb_node *nodes) : nodes_(nodes) { slots_.reserve(HB_MAX_NODES); }
-    size_t size() const { return slots_.size(); }
+    BranchHeap() = default;
+    size_t size() const { return n_; }
 
-    void push(uint16_t id) {
-        slots_.push_back(id);
-        bubble_up(slots_.size() - 1);
+    void push(uint16_t id, uint64_t weight) {
+        slots_[n_] = Slot{weight, id};
+        bubble_up(n_++);
     }
 
     uint16_t pop_min() {
-        uint16_t last = slots_.back();
-        slots_.pop_back();
-        if (slots_.empty()) return last;
-        uint16_t top = slots_[0];
+        const Slot last = slots_[--n_];
+        if (n_ == 0) return last.id;
+        const uint16_t top = slots_[0].id;
         // std: put the former last element at the root, walk the hole down to a leaf position taking the
         // child that is >= its sibling in heap order (the right one on equal weights), then bubble up.
-        size_t hole = 0, n = slots_.size();
+        size_t hole = 0;
+        const size_t n = n_;
         for (;;) {
-            size_t l = 2 * hole + 1, r = l + 1;
+            const size_t l = 2 * hole + 1, r = l + 1;
             if (r < n) {
-                size_t pick = (w(slots_[l]) >= w(slots_[r])) ? r : l;
+                const size_t pick = l + static_cast<size_t>(slots_[l].w >= slots_[r].w);   // branch-free: data-random
                 slots_[hole] = slots_[pick];
                 hole = pick;
             } else if (l < n) {
@@ -56,19 +56,19 @@ public:
     }
 
 private:
-    uint64_t w(uint16_t id) const { return nodes_[id].weight; }
+    struct Slot { uint64_t w; uint16_t id; };        // the weight travels with the id: no indirection per comparison
     void bubble_up(size_t pos) {
-        uint16_t moving = slots_[pos];
+        const Slot moving = slots_[pos];
         while (pos > 0) {
-            size_t parent = (pos - 1) / 2;
-            if (w(moving) >= w(slots_[parent])) break;   // std sift_up: stop when element <= parent in heap order
+            const size_t parent = (pos - 1) / 2;
+            if (moving.w >= slots_[parent].w) break;     // std sift_up: stop when element <= parent in heap order
             slots_[pos] = slots_[parent];
             pos = parent;
         }
         slots_[pos] = moving;
     }
-    const hb_node *nodes_;
-    std::vector<uint16_t> slots_;
+    Slot slots_[HB_MAX_LEAVES + 1];                      // at most one slot per leaf is ever live
+    size_t n_ = 0;
 };
 
 bool is_leaf(const hb_node &n) { return n.left == HB_NO_CHILD; }
@@ -87,39 +87,33 @@ void fill_code_table(hb_tree *t) {
         t->code[root.letter] = 0;
         t->n_leaves = 1;
     } else {
-        struct Frame { uint16_t node; uint16_t depth; };
-        std::vector<Frame> todo;
-        std::vector<uint8_t> path(HB_MAX_LEAVES + 1, 0);
-        todo.push_back({static_cast<uint16_t>(t->root), 0});
-        // each frame carries the branch bit that led to it in path[depth-1], written when the frame is popped
-        std::vector<uint8_t> bit_of(HB_MAX_NODES, 0);
-        while (!todo.empty()) {
-            Frame f = todo.back();
-            todo.pop_back();
-            if (f.depth > 0) path[f.depth - 1] = bit_of[f.node];
+        // the frame carries its code (valid while depth <= 64; deeper codes are stored as 0, only their length counts)
+        struct Frame { uint16_t node; uint16_t depth; uint64_t code; };
+        Frame todo[HB_MAX_LEAVES + 2];                   // pending right siblings along one root-to-leaf path (+ 1)
+        int top = 0;
+        todo[top++] = Frame{static_cast<uint16_t>(t->root), 0, 0};
+        while (top > 0) {
+            const Frame f = todo[--top];
             const hb_node &nd = t->nodes[f.node];
             if (is_leaf(nd)) {
                 t->n_leaves++;
                 t->has_code[nd.letter] = 1;
                 t->code_len[nd.letter] = f.depth;
-                uint64_t c = 0;
-                if (f.depth <= 64)
-                    for (uint16_t k = 0; k < f.depth; k++) c = (c << 1) | path[k];
-                t->code[nd.letter] = c;          // later visits overwrite earlier ones (HashMap::insert)
+                t->code[nd.letter] = f.depth <= 64 ? f.code : 0;   // later visits overwrite earlier ones (HashMap::insert)
                 continue;
             }
-            bit_of[nd.right] = 1;
-            bit_of[nd.left] = 0;
-            todo.push_back({nd.right, static_cast<uint16_t>(f.depth + 1)});   // popped second
-            todo.push_back({nd.left, static_cast<uint16_t>(f.depth + 1)});    // popped first
+            const uint16_t d = static_cast<uint16_t>(f.depth + 1);
+            todo[top++] = Frame{nd.right, d, (f.code << 1) | 1u};     // popped second
+            todo[top++] = Frame{nd.left, d, f.code << 1};             // popped first
         }
     }
-    uint32_t mx = 0, mn = 0xFFFFFFFFu, g = 0;
+    uint32_t mx = 0, mn = 0xFFFFFFFFu, g = 0, last = 0;
     for (int b = 0; b < 256; b++)
         if (t->has_code[b]) {
-            mx = std::max<uint32_t>(mx, t->code_len[b]);
-            mn = std::min<uint32_t>(mn, t->code_len[b]);
-            g = std::gcd(g, static_cast<uint32_t>(t->code_len[b]));
+            const uint32_t len = t->code_len[b];
+            mx = std::max<uint32_t>(mx, len);
+            mn = std::min<uint32_t>(mn, len);
+            if (len != last) { g = std::gcd(g, len); last = len; }    // gcd only when the length changes
         }
     t->max_len = mx;
     t->min_len = mn;
@@ -145,13 +139,13 @@ hb_status hb_tree_from_pairs(const uint8_t *letters, const uint64_t *weights, si
     if (n == 0) return HB_ERR_EMPTY_WEIGHTS;              // tree_inner.rs:283-285
     if (n > HB_MAX_LEAVES) return HB_ERR_INVALID_ARG;
     std::memset(tree, 0, sizeof *tree);
-    BranchHeap heap(tree->nodes);
+    BranchHeap heap;
     for (size_t i = 0; i < n; i++) {                      // branch_heap.rs:52-58
         hb_node &nd = tree->nodes[tree->n_nodes];
         nd.left = nd.right = HB_NO_CHILD;
         nd.letter = letters[i];
         nd.weight = weights[i];
-        heap.push(static_cast<uint16_t>(tree->n_nodes++));
+        heap.push(static_cast<uint16_t>(tree->n_nodes++), nd.weight);
     }
     while (heap.size() > 1) {                             // tree_inner.rs:289-303
         uint16_t lo = heap.pop_min();
@@ -161,7 +155,7 @@ hb_status hb_tree_from_pairs(const uint8_t *letters, const uint64_t *weights, si
         nd.right = next;
         nd.letter = 0;
         nd.weight = tree->nodes[lo].weight + tree->nodes[next].weight;
-        heap.push(static_cast<uint16_t>(tree->n_nodes++));
+        heap.push(static_cast<uint16_t>(tree->n_nodes++), nd.weight);
     }
     tree->root = heap.pop_min();                          // tree_inner.rs:306
     fill_code_table(tree);

@@ -88,6 +88,7 @@ SYMBOLS = [
     ("hb_decompress_u8_into", C.c_int, [_vp, _vp, C.c_size_t, C.c_uint8, _treep, _vp, C.c_size_t, _szp]),
     ("hb_histogram_u8_dev", C.c_int, [_vp, _vp, C.c_size_t, _vp]),
     ("hb_stream_bits", C.c_int, [_u64p, _treep, _u64p, _u8p]),
+    ("hb_shard_plan", C.c_int, [_u64p, C.c_size_t, C.c_int, _treep, _u64p]),
     ("hb_encode_u8_dev", C.c_int, [_vp, _vp, C.c_size_t, _treep, C.c_uint32, _vp, C.c_size_t, _vp]),
     ("hb_compress_u8_dev", C.c_int, [_vp, _vp, C.c_size_t, C.c_int, _treep, _vp, C.c_size_t, _szp, _u8p]),
     ("hb_decompress_u8_dev", C.c_int, [_vp, _vp, C.c_size_t, C.c_uint8, _treep, _vp, C.c_size_t, _szp]),

@@ -191,6 +191,21 @@ hb_status hb_stream_bits(const uint64_t weights[256], const hb_tree *tree, uint6
     return HB_OK;
 }
 
+hb_status hb_shard_plan(const uint64_t *hists, size_t n_shards, int order_mode, hb_tree *tree_out, uint64_t *shard_bits) {
+    if (!hists || !n_shards || !tree_out || !shard_bits) return HB_ERR_INVALID_ARG;
+    uint64_t total[256] = {0};
+    for (size_t g = 0; g < n_shards; g++)
+        for (int b = 0; b < 256; b++) total[b] += hists[g * 256 + b];
+    const hb_status st = hb_tree_from_weights(total, order_mode, tree_out);
+    if (st != HB_OK) return st;
+    for (size_t g = 0; g < n_shards; g++) {
+        uint64_t bits = 0;
+        for (int b = 0; b < 256; b++) bits += hists[g * 256 + b] * tree_out->code_len[b];
+        shard_bits[g] = bits;
+    }
+    return HB_OK;
+}
+
 hb_status hb_tree_as_bin(const hb_tree *tree, uint8_t *out, size_t cap_bytes, size_t *n_bits) {
     if (!tree || !out || !n_bits) return HB_ERR_INVALID_ARG;
     BitSink sink{out, cap_bytes * 8};

@@ -133,6 +133,15 @@ class Engine:
     def tree_from_histogram(self, hist: torch.Tensor, order: int = L.HB_ORDER_ASC) -> HuffTree:
         return self.tree_from_weights(hist.cpu().numpy(), order)
 
+    def shard_plan(self, hists, order: int = L.HB_ORDER_ASC):
+        """Multi-GPU plan (hb_shard_plan): (G, 256) gathered histograms -> (tree of their sum, [bits of every shard])."""
+        h = np.ascontiguousarray(hists)
+        h = h.view(np.uint64) if h.dtype == np.int64 else h.astype(np.uint64, copy=False)
+        t = L.HbTree()
+        bits = (C.c_uint64 * h.shape[0])()
+        _raise(self.lib.hb_shard_plan(h.ctypes.data_as(C.POINTER(C.c_uint64)), h.shape[0], order, C.byref(t), bits))
+        return HuffTree(t), list(bits)
+
     def tree_from_weights(self, weights, order: int = L.HB_ORDER_ASC) -> HuffTree:
         w = np.ascontiguousarray(np.asarray(weights).astype(np.uint64))
         t = L.HbTree()

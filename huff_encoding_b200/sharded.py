@@ -54,13 +54,11 @@ class ShardedCodec:
                 parts = [torch.zeros_like(local) for _ in range(self.world)]
                 dist.all_gather(parts, local)
                 self._gathered.copy_(torch.stack(parts))
-            h = self._gathered.cpu().numpy().astype(np.uint64)          # host sync: the tree needs the histogram
+            h = self._gathered.cpu().numpy()                            # host sync: the tree needs the histogram
         else:
-            h = local.cpu().numpy().astype(np.uint64)[None, :]
-        global_w = h.sum(axis=0)
-        tree = eng.tree_from_weights(global_w)
-        lens = np.frombuffer(tree.raw.code_len, dtype=np.uint16).astype(np.uint64)
-        all_bits = [int(x) for x in (h * lens[None, :]).sum(axis=1)]
+            h = local.cpu().numpy()[None, :]
+        # one host call (hb_shard_plan): tree of the summed histogram + every shard's bit total
+        tree, all_bits = eng.shard_plan(h)
         my_bits = all_bits[self.rank]
         offset = sum(all_bits[: self.rank])
         total = sum(all_bits)

@@ -142,6 +142,10 @@ hb_status hb_decompress_u8_into(hb_ctx *ctx, const uint8_t *comp, size_t comp_le
 hb_status hb_histogram_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, uint64_t *d_hist256);
 /* Exact stream size for (histogram, tree): sum w[b] * len[b].  Host arithmetic. */
 hb_status hb_stream_bits(const uint64_t weights[256], const hb_tree *tree, uint64_t *bits, uint8_t *missing);
+/* Multi-GPU plan, host arithmetic: from the G gathered shard histograms (hists[g*256 + b]) build the tree of
+ * their sum (= the tree one GPU would build for the whole input) and every shard's exact bit total
+ * shard_bits[g] = sum_b hists[g][b] * len[b]; the exclusive scan of shard_bits is each shard's global bit offset. */
+hb_status hb_shard_plan(const uint64_t *hists, size_t n_shards, int order_mode, hb_tree *tree_out, uint64_t *shard_bits);
 /* Encoder proper = compress_with_tree's packing loop (comp.rs:422-447).
  * The encoder needs the per-region histograms hb_histogram_u8_dev produces as a by-product.  If the immediately
  * preceding histogram call on this ctx was for the same (d_data, n) they are reused; otherwise the histogram kernel is

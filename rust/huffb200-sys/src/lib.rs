@@ -80,4 +80,46 @@ extern "C" {
                                     missing: *mut u8) -> c_int;
     pub fn hb_decompress_u8(ctx: *mut hb_ctx, comp: *const u8, comp_len: usize, padding_bits: u8,
                             tree: *const hb_tree, out: *mut *mut u8, out_n: *mut usize) -> c_int;
+
+    // caller-owned (ideally pinned, hb_host_alloc) buffers: no allocation inside the call
+    pub fn hb_host_alloc(bytes: usize, p: *mut *mut c_void) -> c_int;
+    pub fn hb_host_free(p: *mut c_void);
+    pub fn hb_compress_u8_into(ctx: *mut hb_ctx, data: *const u8, n: usize, order_mode: c_int, tree_out: *mut hb_tree,
+                               comp_bytes: *mut u8, comp_cap: usize, comp_len: *mut usize, padding_bits: *mut u8) -> c_int;
+    pub fn hb_compress_with_tree_u8_into(ctx: *mut hb_ctx, data: *const u8, n: usize, tree: *const hb_tree,
+                                         comp_bytes: *mut u8, comp_cap: usize, comp_len: *mut usize,
+                                         padding_bits: *mut u8, missing: *mut u8) -> c_int;
+    pub fn hb_decompress_u8_into(ctx: *mut hb_ctx, comp: *const u8, comp_len: usize, padding_bits: u8,
+                                 tree: *const hb_tree, out: *mut u8, out_cap: usize, out_n: *mut usize) -> c_int;
+
+    // context helpers
+    pub fn hb_version() -> c_int;
+    pub fn hb_ctx_sync(ctx: *mut hb_ctx) -> c_int;
+    pub fn hb_ctx_stream(ctx: *mut hb_ctx) -> *mut c_void;
+    pub fn hb_ctx_kernel_launches(ctx: *mut hb_ctx, count: *mut u64) -> c_int;
+    pub fn hb_ctx_last_decode_repairs(ctx: *mut hb_ctx, count: *mut u32) -> c_int;
+
+    // device-buffer API (pointers are CUDA device pointers; everything is enqueued on hb_ctx_stream)
+    pub fn hb_histogram_u8_dev(ctx: *mut hb_ctx, d_data: *const u8, n: usize, d_hist256: *mut u64) -> c_int;
+    pub fn hb_stream_bits(weights: *const u64, tree: *const hb_tree, bits: *mut u64, missing: *mut u8) -> c_int;
+    pub fn hb_shard_plan(hists: *const u64, n_shards: usize, order_mode: c_int, tree_out: *mut hb_tree,
+                         shard_bits: *mut u64) -> c_int;
+    pub fn hb_encode_u8_dev(ctx: *mut hb_ctx, d_data: *const u8, n: usize, tree: *const hb_tree, start_bit: u32,
+                            d_out: *mut u8, out_cap: usize, d_total_bits: *mut u64) -> c_int;
+    pub fn hb_compress_u8_dev(ctx: *mut hb_ctx, d_data: *const u8, n: usize, order_mode: c_int, tree_out: *mut hb_tree,
+                              d_out: *mut u8, out_cap: usize, comp_len: *mut usize, padding_bits: *mut u8) -> c_int;
+    pub fn hb_decompress_u8_dev(ctx: *mut hb_ctx, d_comp: *const u8, comp_len: usize, padding_bits: u8,
+                                tree: *const hb_tree, d_out: *mut u8, out_cap: usize, out_n: *mut usize) -> c_int;
+    pub fn hb_decode_count_dev(ctx: *mut hb_ctx, d_buf: *const u8, avail_bits: u64, own_begin: u64, own_end: u64,
+                               stream_bit0: u64, tree: *const hb_tree, info: *mut hb_shard_info) -> c_int;
+    pub fn hb_decode_write_dev(ctx: *mut hb_ctx, d_out: *mut u8, out_cap: usize) -> c_int;
+}
+
+/// Sharded decode result (include/huffb200.h: hb_shard_info)
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct hb_shard_info {
+    pub entry_bit: i64,
+    pub exit_bit: u64,
+    pub n_letters: u64,
 }

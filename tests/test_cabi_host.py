@@ -152,3 +152,26 @@ def test_no_cpu_fallback_without_a_gpu():
     from huff_encoding_b200 import compress
     with pytest.raises(HuffCudaError):
         compress(b"abbccc")
+
+
+def test_shard_plan_matches_the_per_shard_arithmetic():
+    """hb_shard_plan = tree of the summed histograms + sum_b hist_g[b] * len[b] for every shard."""
+    import ctypes as C
+    from huff_encoding_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(11)
+    for G_ in (1, 2, 3, 8):
+        h = rng.integers(0, 5000, size=(G_, 256)).astype(np.uint64)
+        h[:, rng.integers(0, 256, size=40)] = 0                       # some letters absent everywhere or in some shards
+        t, t_ref = L.HbTree(), L.HbTree()
+        bits = (C.c_uint64 * G_)()
+        assert lib.hb_shard_plan(h.ctypes.data_as(C.POINTER(C.c_uint64)), G_, L.HB_ORDER_ASC, C.byref(t), bits) == L.HB_OK
+        total = np.ascontiguousarray(h.sum(axis=0))
+        assert lib.hb_tree_from_weights(total.ctypes.data_as(C.POINTER(C.c_uint64)), L.HB_ORDER_ASC, C.byref(t_ref)) == L.HB_OK
+        assert bytes(t) == bytes(t_ref)
+        lens = np.frombuffer(t.code_len, dtype=np.uint16).astype(np.uint64)
+        assert list(bits) == [int(x) for x in (h * lens[None, :]).sum(axis=1)]
+    empty = np.zeros((2, 256), dtype=np.uint64)
+    t = L.HbTree()
+    bits = (C.c_uint64 * 2)()
+    assert lib.hb_shard_plan(empty.ctypes.data_as(C.POINTER(C.c_uint64)), 2, L.HB_ORDER_ASC, C.byref(t), bits) == L.HB_ERR_EMPTY_WEIGHTS

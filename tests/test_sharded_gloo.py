@@ -30,6 +30,15 @@ class OracleEngine:
     def histogram(self, data):
         return torch.from_numpy(O.histogram(data.numpy()).astype(np.int64))
 
+    def shard_plan(self, hists, order=0):
+        import ctypes as C
+        from huff_encoding_b200 import _lib as L
+        h = np.ascontiguousarray(np.asarray(hists).astype(np.uint64))
+        t = L.HbTree()
+        bits = (C.c_uint64 * h.shape[0])()
+        assert L.load().hb_shard_plan(h.ctypes.data_as(C.POINTER(C.c_uint64)), h.shape[0], order, C.byref(t), bits) == 0
+        return HuffTree(t), list(bits)                                                # host code of the product library
+
     def tree_from_weights(self, w, order=0):
         return HuffTree.from_weights({b: int(w[b]) for b in range(256) if w[b]})     # host code of the product library
 

@@ -219,6 +219,7 @@ hb_status upload_enc_table(hb_ctx *ctx, const hb_tree *tree) {
         const uint64_t left = len ? tree->code[b] << (64 - len) : 0;       // code left-aligned in 64 bits
         t.lo[b] = make_uint2(static_cast<uint32_t>(left >> 32), len);
         t.hi[b] = static_cast<uint32_t>(left);
+        t.packed[b] = len <= 16 ? ((static_cast<uint32_t>(left >> 32) & 0xFFFF0000u) | len) : 0u;
         max_len = std::max(max_len, len);
     }
     HB_CUDA(cudaMemcpyAsync(ctx->d_enc_table, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream));

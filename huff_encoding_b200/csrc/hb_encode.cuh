@@ -43,15 +43,25 @@ static_assert(kEncRoundLetters % (kEncWarps * enc_tile_letters(4)) == 0 && kEncR
 struct EncTable {
     uint2 lo[256];        // (first min(len, 32) code bits, left-aligned in 32 bits; len)
     uint32_t hi[256];     // the remaining len - 32 bits, left-aligned (len > 32 only)
+    uint32_t packed[256]; // len <= 16 only: code left-aligned in the upper half | len  (one 32-bit lookup; else 0)
 };
 
-// S == 4 (the hot variant) pins the lane-replicated table at the ABSOLUTE shared address 0x10000: entry (b, lane)
-// is then at 0x10000 | b << 8 | lane << 3, which ONE byte-permute builds from the raw input word (no shift, mask,
-// add).  The shared memory below 0x10000 (minus the static variables) is left unused; the staging follows the table.
+// S == 4 (the hot variant) looks letters up in a lane-replicated table of PACKED 32-bit entries (code << 16 | len: one
+// shared-memory wavefront per warp lookup instead of two) pinned at the ABSOLUTE shared address 0x10000 with 256 bytes
+// per letter: entry (b, lane) is at 0x10000 | b << 8 | lane << 2, which ONE byte-permute builds from the raw input
+// word (no shift, mask, add).  The shared memory below 0x10000 (minus the static variables) is left unused; the
+// staging and a plain 2 KiB (code, len) table for the once-per-tile lookups follow the table.
 constexpr uint32_t kEncTabAbs = 0x10000u;
+constexpr size_t kEncPackedBytes = 256 * 256;
 constexpr size_t enc_smem_bytes(int S) {
-    return (S == 4 ? static_cast<size_t>(kEncTabAbs) : 0) + 256 * 32 * sizeof(uint2) + (S == 1 ? 256 * sizeof(uint32_t) : 0) +
+    return (S == 4 ? static_cast<size_t>(kEncTabAbs) + kEncPackedBytes + 256 * sizeof(uint2)
+                   : 256 * 32 * sizeof(uint2) + (S == 1 ? 256 * sizeof(uint32_t) : 0)) +
            static_cast<size_t>(kEncWarps) * enc_stage_words(S) * sizeof(uint32_t);
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
+    return r;
 }
 __device__ __forceinline__ uint2 lds_u2(uint32_t a) {
     uint2 r;
@@ -61,10 +71,10 @@ __device__ __forceinline__ uint2 lds_u2(uint32_t a) {
 
 // exact bit count of a region from its histogram: sum_b hist[b] * len[b]  (block-wide, all threads get the result)
 __device__ __forceinline__ unsigned long long enc_region_base(const uint32_t *__restrict__ region_hist, uint32_t n_before,
-                                                              const uint2 *s_tab_lane0, unsigned long long *s_red) {
+                                                              const uint2 *s_tab_lane0, int tab_shift, unsigned long long *s_red) {
     unsigned long long acc = 0;
     for (uint32_t k = threadIdx.x; k < n_before * 256u; k += blockDim.x)
-        acc += static_cast<unsigned long long>(region_hist[k]) * s_tab_lane0[(k & 255u) << 5].y;
+        acc += static_cast<unsigned long long>(region_hist[k]) * s_tab_lane0[(k & 255u) << tab_shift].y;
 #pragma unroll
     for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, sft);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
@@ -115,7 +125,8 @@ template <int S>
 __device__ __noinline__ uint32_t enc_partial_bits(const uint8_t *__restrict__ data, size_t lane_base, uint32_t n_mine,
                                                   const uint2 *my_tab) {
     uint32_t bits = 0;
-    for (uint32_t j = 0; j < n_mine; j++) bits += my_tab[static_cast<uint32_t>(data[lane_base + j]) << 5].y;
+    constexpr int kTabShift = S == 4 ? 0 : 5;
+    for (uint32_t j = 0; j < n_mine; j++) bits += my_tab[static_cast<uint32_t>(data[lane_base + j]) << kTabShift].y;
     return bits;
 }
 template <int S>
@@ -125,9 +136,10 @@ __device__ __noinline__ void enc_partial_append(const uint8_t *__restrict__ data
     pk.ptr = ptr;
     pk.fill = fill;
     pk.hi = 0;
+    constexpr int kTabShift = S == 4 ? 0 : 5;
     for (uint32_t j = 0; j < n_mine; j++) {
         const uint32_t b = data[lane_base + j];
-        const uint2 e = my_tab[b << 5];
+        const uint2 e = my_tab[b << kTabShift];
         pk.append(e.x, min(e.y, 32u));
         if (S == 1 && e.y > 32) pk.append(s_hi[b], e.y - 32);
     }
@@ -144,16 +156,24 @@ encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable
     constexpr int kPieces = 16;                                  // register-held pieces per lane
     constexpr int kStageWords = enc_stage_words(S);
 
-    // S == 4: the table sits at absolute shared address kEncTabAbs (see enc_smem_bytes)
+    // S == 4: packed lane-replicated table at absolute shared address kEncTabAbs, then a plain [256] (code, len) table;
+    // else: lane-replicated (code, len) table [256][32] at the start (+ the code tails for S == 1).  See enc_smem_bytes.
+    constexpr int kTabShift = S == 4 ? 0 : 5;                   // index shift of the (code, len) table
     uint8_t *tab_bytes = enc_smem + (S == 4 ? kEncTabAbs - smem_addr(enc_smem) : 0u);
-    uint2 *s_tab = reinterpret_cast<uint2 *>(tab_bytes);                                    // [256][32]
-    uint32_t *s_hi = reinterpret_cast<uint32_t *>(tab_bytes + 256 * 32 * sizeof(uint2));    // [256] (S == 1)
+    uint2 *s_tab = reinterpret_cast<uint2 *>(tab_bytes + (S == 4 ? kEncPackedBytes : 0));
+    uint32_t *s_hi = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_tab) + (S == 4 ? 256 : 256 * 32) * sizeof(uint2));   // [256] (S == 1)
     uint32_t *s_stage_all = s_hi + (S == 1 ? 256 : 0);
     __shared__ unsigned long long s_red[kEncWarps];
     __shared__ uint32_t s_tile_bits[2][kEncWarps];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 256 * 32; i += kEncThreads) s_tab[i] = table->lo[i >> 5];
+    if (S == 4) {
+        uint32_t *packed = reinterpret_cast<uint32_t *>(tab_bytes);
+        for (int i = threadIdx.x; i < 256 * 32; i += kEncThreads) packed[(i >> 5) * 64 + (i & 31)] = table->packed[i >> 5];
+        for (int i = threadIdx.x; i < 256; i += kEncThreads) s_tab[i] = table->lo[i];
+    } else {
+        for (int i = threadIdx.x; i < 256 * 32; i += kEncThreads) s_tab[i] = table->lo[i >> 5];
+    }
     if (S == 1) for (int i = threadIdx.x; i < 256; i += kEncThreads) s_hi[i] = table->hi[i];
     __syncthreads();
 
@@ -161,11 +181,11 @@ encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable
     if (region_begin >= n) return;
     const size_t region_end = min(n, region_begin + region_letters);
     // global bit offset of this region: everything the regions before it emit (+ the caller's start bit)
-    unsigned long long running = start_bit + enc_region_base(region_hist, blockIdx.x, s_tab, s_red);
+    unsigned long long running = start_bit + enc_region_base(region_hist, blockIdx.x, s_tab, kTabShift, s_red);
 
     uint32_t *stage = s_stage_all + warp * kStageWords;         // word m = global stream word (tile offset / 32) + m
     const bool aligned32 = (reinterpret_cast<uintptr_t>(data) & 31) == 0;
-    const uint2 *my_tab = s_tab + lane;
+    const uint2 *my_tab = s_tab + (S == 4 ? 0 : lane);
     const uint32_t n_rounds = static_cast<uint32_t>((region_end - region_begin + kEncWarps * kTile - 1) / (kEncWarps * kTile));
 
     // this lane's letters of a full tile: one 256-bit load (or 128-bit loads)
@@ -214,16 +234,18 @@ encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable
             if (!kPipelined) load_raw(lane_base);
             if (S == 4) {
                 // quads: four letters -> one <= 64-bit piece (qh:ql, left-aligned) and its length
-                const uint32_t lane_addr = kEncTabAbs + (static_cast<uint32_t>(lane) << 3);
+                const uint32_t lane_addr = kEncTabAbs + (static_cast<uint32_t>(lane) << 2);
+                constexpr uint32_t kCode = 0xFFFF0000u;
 #pragma unroll
                 for (int q = 0; q < 8; q++) {
                     const uint32_t w = raw[q];
-                    const uint2 e0 = lds_u2(__byte_perm(w, lane_addr, 0x7604));     // 0x10000 | byte << 8 | lane << 3
-                    const uint2 e1 = lds_u2(__byte_perm(w, lane_addr, 0x7614));
-                    const uint2 e2 = lds_u2(__byte_perm(w, lane_addr, 0x7624));
-                    const uint2 e3 = lds_u2(__byte_perm(w, lane_addr, 0x7634));
-                    const uint32_t v01 = e0.x | (e1.x >> e0.y), l01 = e0.y + e1.y;  // codes <= 16 bits
-                    const uint32_t v23 = e2.x | (e3.x >> e2.y), l23 = e2.y + e3.y;
+                    const uint32_t e0 = lds_u32(__byte_perm(w, lane_addr, 0x7604));   // 0x10000 | byte << 8 | lane << 2
+                    const uint32_t e1 = lds_u32(__byte_perm(w, lane_addr, 0x7614));
+                    const uint32_t e2 = lds_u32(__byte_perm(w, lane_addr, 0x7624));
+                    const uint32_t e3 = lds_u32(__byte_perm(w, lane_addr, 0x7634));
+                    // entry = code << 16 | len (len <= 16): the wrapping funnel shift takes len from the low 5 bits
+                    const uint32_t v01 = (e0 & kCode) | __funnelshift_r(e1 & kCode, 0u, e0), l01 = (e0 + e1) & 0x3Fu;
+                    const uint32_t v23 = (e2 & kCode) | __funnelshift_r(e3 & kCode, 0u, e2), l23 = (e2 + e3) & 0x3Fu;
                     pv[2 * q] = v01 | __funnelshift_rc(v23, 0u, l01);
                     pv[2 * q + 1] = __funnelshift_rc(0u, v23, l01);
                     plen[q] = l01 + l23;
@@ -238,7 +260,7 @@ encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable
 #pragma unroll
                 for (int k = 0; k < kPieces; k++) {
                     const uint32_t b = (raw[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-                    const uint2 e = my_tab[b << 5];
+                    const uint2 e = my_tab[b << kTabShift];
                     pv[k] = e.x;
                     plen[k >> 2] |= e.y << (8 * (k & 3));      // S == 1: up to 64, the second piece comes from s_hi
                     lane_bits += e.y;
@@ -277,7 +299,7 @@ encode_regions_kernel(const uint8_t *__restrict__ data, size_t n, const EncTable
         uint32_t pred_tail = 0;
         if (tile_base > 0) {
             const uint32_t b = pred_letter;
-            const uint2 e = my_tab[b << 5];
+            const uint2 e = my_tab[b << kTabShift];
             // suffix sum of the lengths of the letters after mine
             uint32_t after = e.y;
 #pragma unroll

@@ -14,8 +14,9 @@
 //       verify   entry[t] must equal exit[t-1]; threads whose candidate was wrong adopt exit[t-1] and redo B.
 //                Iterated to a fixed point inside the CTA (terminates: thread t is final after t rounds).
 //   chain check  (dec_verify_kernel) the same test across CTA boundaries; mismatching CTAs are re-run serially
-//                with the corrected entry by dec_fix_kernel (rare: needs a code that fails to resynchronise
-//                within a whole 1024-bit halo; worst case = strictly sequential propagation, still exact).
+//                with the corrected entry by dec_fix_kernel (rare: a CTA's first thread looks back 384 bits, and the
+//                measured miss rate falls ~27x per 64 bits from 1e-4 at 192; worst case = strictly sequential
+//                propagation, still exact).
 //   offsets      two small scan kernels turn per-CTA letter counts into 64-bit output offsets.
 //   write pass   (dec_write_kernel)  no shared-memory staging of the output: thread t owns the output bytes between
 //                the 32-byte boundaries at or after its first letter and at or after its successor's first letter.  It
@@ -23,9 +24,11 @@
 //                predecessor writes), packs 32 letters into eight registers with static byte inserts and stores one
 //                full 32-byte sector per lane with a 256-bit store (gap-free rewrite, every sector written once).
 //
-// Decoding uses a 12-bit first-level table (letter, length) with a tree walk behind it for longer codes (any depth),
-// and for the count pass a 12-bit multi-letter table (bits consumed, letters completed) that skips several
-// short codes per lookup.  Lookups and stream words come from shared memory (stream rows padded by one word per
+// Decoding uses a 12-bit first-level table (letter, length), a second-level table for codes of 13..20 bits (one
+// 256-entry table per tree node at depth 12, in global memory, read through L1 by those codes only) and a tree walk
+// behind it for longer codes (any depth); the count pass adds a 13-bit multi-letter table (bits consumed, letters
+// completed) that skips several short codes per lookup.  Both passes come in two instances, chosen per launch by the
+// tree's longest code: the common one has no tests for codes the tables do not cover.  Lookups and stream words come from shared memory (stream rows padded by one word per
 // 32 so that threads walking their own subsequence in lock step hit 32 different banks).  The inner loops keep a
 // 64-bit bit window in registers and address shared memory through 32-bit shared-space pointers.
 //
@@ -39,9 +42,6 @@ namespace hb {
 
 #ifndef HB_DEC_THREADS
 #define HB_DEC_THREADS 256
-#endif
-#ifndef HB_COUNT_UNROLL
-#define HB_COUNT_UNROLL 2
 #endif
 #ifndef HB_LEAD_LOOKBACK_BITS
 #define HB_LEAD_LOOKBACK_BITS 384        // look-back of a CTA's first thread (nobody verifies it inside the CTA)
@@ -66,7 +66,7 @@ constexpr int kCntBitsMax = 14;
 constexpr uint32_t kEnd32 = 0xFFFFFFFFu;
 constexpr uint64_t kEnd64 = ~0ull;
 constexpr int kLeadLookbackBits = HB_LEAD_LOOKBACK_BITS;
-constexpr int kLookbackBits = HB_LOOKBACK_BITS;                             // in-CTA look-back window W (thread 0 uses the full halo);
+constexpr int kLookbackBits = HB_LOOKBACK_BITS;                             // in-CTA look-back window W (a CTA's first thread: kLeadLookbackBits);
                                                                // measured resynchronisation distance: mean 16, p99 < 90 bits
 constexpr int kScanGroup = 1024;                               // CTAs per offset-scan group
 constexpr int kGroup = 32;                                     // letters per 256-bit store in the write pass
@@ -92,7 +92,7 @@ struct DecParams {
     uint64_t stream_bit0;              // stream bit index of buffer bit 0 (phase of the gcd alignment)
     uint32_t len_gcd, fixed_len;       // gcd of code lengths; fixed_len != 0 when all codes have that length
     uint32_t max_len;                  // longest code (bounds how far a thread may read past its subsequence)
-    uint32_t cnt_bits;                 // index width of DecTables::cnt in use (12..14)
+    uint32_t cnt_bits;                 // index width of DecTables::cnt in use (= kCntBits)
     uint32_t spoil_speculation;        // test hook: CTA-leading threads skip their look-back (forces the repair path)
     uint32_t first_block, n_blocks;    // CTAs cover chunks first_block .. first_block + n_blocks - 1
     uint32_t *sub_info;                // per subsequence (relative to first_block): entry_rel << 16 | count

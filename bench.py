@@ -312,6 +312,22 @@ def run_ours(args):
                    "comp_bytes": zc, "phase_ms": {k: round(v, 4) for k, v in gphase.items()},
                    "alg_bytes": {"hist": n, "encode": n + zc, "dec_count": zc, "dec_write": zc + n}}
         del zdata
+        # a long-tailed input (Zipf(1.5): codes up to 14 bits, 1.5 % of the letters beyond the 12-bit decode table):
+        # the decoder instances for trees with long codes
+        ldata = make_workload("zipf15", n, rank * n, dev)
+        lphase = {k: 0.0 for k in phases}
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                codec.round_trip(ldata, comp_buf, out_buf)
+            stream.synchronize()
+            lm = [codec.round_trip(ldata, comp_buf, out_buf, want_events=True) for _ in range(gsteps)]
+            stream.synchronize()
+        assert torch.equal(out_buf[:n], ldata), "long-code round trip mismatch"
+        for m in lm:
+            for k in phases:
+                lphase[k] += m[k][0].elapsed_time(m[k][1]) / gsteps
+        general["zipf15_long_codes_phase_ms"] = {k: round(v, 4) for k, v in lphase.items()}
+        del ldata
         # the same uniform input forced through the general kernels (fast path off): what configs[1] costs without it
         os.environ["HB_NO_FASTPATH"] = "1"
         try:

@@ -648,8 +648,11 @@ __device__ __noinline__ uint32_t slow_next(LetterSource &src) {
 }
 
 // 32 letters from the register bit window, one table lookup each, static byte inserts, one 256-bit store.
-// kResolve = false: branch-free body for trees without codes longer than the first-level table (the CTA-uniform
+// kResolve = false: branch-free body for trees without codes longer than the first-level table (the launch-uniform
 // common case).  kResolve = true: a first-level miss is resolved per letter in the second-level table (13..20 bits).
+// (Measured alternatives for kResolve: testing once per four letters and redoing the quad -- a long entry has length 0
+// and repeats itself, so one test finds it -- is 3x SLOWER at 1.5 % long letters: some lane of the warp hits one in
+// 86 % of the quads; an optimistic whole-group attempt is worse still.)
 // Returns false with nothing stored and `reader` untouched when a code is longer than the tables cover; the caller
 // then redoes the group letter by letter.
 template <bool kResolve>
@@ -658,25 +661,28 @@ __device__ __forceinline__ bool dec_fast_group(const DecShared &sh, BitReader &r
     uint32_t v[8];
     uint32_t escape = 0;
 #pragma unroll
-    for (int j = 0; j < kGroup; j++) {
-        uint32_t e = lds16(sh.lut + rd.peek_lut_off());
-        if (kResolve) {
-            if (lut_is_long(e)) e = lut_resolve(sh, e, rd);               // rare, divergent
-            escape |= e;                                                  // (no long entries exist when !kResolve)
+    for (int q = 0; q < kGroup / 4; q++) {
+        uint32_t e[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            e[k] = lds16(sh.lut + rd.peek_lut_off());
+            if (kResolve) {
+                if (lut_is_long(e[k])) e[k] = lut_resolve(sh, e[k], rd);  // rare, divergent
+                escape |= e[k];                                           // (no long entries exist when !kResolve)
+            }
+            // consume (the stream position rd.q is recomputed after the group)
+            rd.s += lut_len(e[k]);
+            if (rd.s >= 32) {
+                rd.s -= 32;
+                rd.w0 = rd.w1;
+                rd.w1 = lds32(win_word_addr(sh.win, rd.wi));
+                rd.wi++;
+            }
         }
-        // consume (the stream position rd.q is recomputed after the group)
-        rd.s += lut_len(e);
-        if (rd.s >= 32) {
-            rd.s -= 32;
-            rd.w0 = rd.w1;
-            rd.w1 = lds32(win_word_addr(sh.win, rd.wi));
-            rd.wi++;
-        }
-        // the letter sits in byte 0 of e: one PRMT drops it into byte j%4 of the output word
-        if ((j & 3) == 0) v[j >> 2] = __byte_perm(e, 0u, 0x4440);
-        else if ((j & 3) == 1) v[j >> 2] = __byte_perm(v[j >> 2], e, 0x3240);
-        else if ((j & 3) == 2) v[j >> 2] = __byte_perm(v[j >> 2], e, 0x3410);
-        else v[j >> 2] = __byte_perm(v[j >> 2], e, 0x4210);
+        // the letter sits in byte 0 of an entry: three PRMTs gather four letters into one output word
+        uint32_t w = __byte_perm(e[0], e[1], 0x4440);       // bytes 0, 1 (bytes 2, 3 are replaced next)
+        w = __byte_perm(w, e[2], 0x3410);
+        v[q] = __byte_perm(w, e[3], 0x4210);
     }
     if (lut_is_long(escape)) return false;
     rd.q = ((rd.wi - 2) << 5) + rd.s;

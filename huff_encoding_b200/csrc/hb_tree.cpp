@@ -107,14 +107,18 @@ void fill_code_table(hb_tree *t) {
             todo[top++] = Frame{nd.left, d, f.code << 1};             // popped first
         }
     }
-    uint32_t mx = 0, mn = 0xFFFFFFFFu, g = 0, last = 0;
+    // longest / shortest code and the gcd of all lengths (gcd over the DISTINCT lengths: at most a few dozen)
+    uint32_t mx = 0, mn = 0xFFFFFFFFu, g = 0;
+    uint64_t seen[5] = {0, 0, 0, 0, 0};                    // lengths 0..319 (a tree has at most 257 leaves)
     for (int b = 0; b < 256; b++)
         if (t->has_code[b]) {
             const uint32_t len = t->code_len[b];
             mx = std::max<uint32_t>(mx, len);
             mn = std::min<uint32_t>(mn, len);
-            if (len != last) { g = std::gcd(g, len); last = len; }    // gcd only when the length changes
+            if (len < 320) seen[len >> 6] |= 1ull << (len & 63); else g = std::gcd(g, len);
         }
+    for (uint32_t len = 1; len < 320 && len <= mx; len++)
+        if (seen[len >> 6] >> (len & 63) & 1) g = std::gcd(g, len);
     t->max_len = mx;
     t->min_len = mn;
     t->len_gcd = g;

@@ -138,7 +138,6 @@ struct BitReader {
         w1 = lds32(win_word_addr(win, wi + 1));
         wi += 2;
     }
-    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(w1, w0, s) >> (32 - kLutBits); }
     // byte offset of the first-level entry for the next kLutBits bits (mask + one LEA.HI with the table base)
     // (the AND is opaque to the optimiser, which would otherwise turn it back into shift + mask + add)
     __device__ __forceinline__ uint32_t peek_lut_off() const {
@@ -146,19 +145,8 @@ struct BitReader {
         asm("and.b32 %0, %1, %2;" : "=r"(y) : "r"(__funnelshift_l(w1, w0, s)), "n"(~((1u << (32 - kLutBits)) - 1u)));
         return y >> (31 - kLutBits);
     }
-    __device__ __forceinline__ uint32_t peek_bits(uint32_t k) const { return __funnelshift_l(w1, w0, s) >> (32 - k); }
     __device__ __forceinline__ void consume(uint32_t win, uint32_t l) {  // l < 32; leaves q stale (see users)
         s += l;
-        if (s >= 32) {
-            s -= 32;
-            w0 = w1;
-            w1 = lds32(win_word_addr(win, wi));
-            wi++;
-        }
-    }
-    __device__ __forceinline__ void skip(uint32_t win, uint32_t l) {  // l < 32
-        s += l;
-        q += l;
         if (s >= 32) {
             s -= 32;
             w0 = w1;

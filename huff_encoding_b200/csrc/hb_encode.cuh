@@ -63,11 +63,6 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
     return r;
 }
-__device__ __forceinline__ uint2 lds_u2(uint32_t a) {
-    uint2 r;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a));
-    return r;
-}
 
 // exact bit count of a region from its histogram: sum_b hist[b] * len[b]  (block-wide, all threads get the result)
 __device__ __forceinline__ unsigned long long enc_region_base(const uint32_t *__restrict__ region_hist, uint32_t n_before,

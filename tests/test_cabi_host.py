@@ -175,3 +175,46 @@ def test_shard_plan_matches_the_per_shard_arithmetic():
     t = L.HbTree()
     bits = (C.c_uint64 * 2)()
     assert lib.hb_shard_plan(empty.ctypes.data_as(C.POINTER(C.c_uint64)), 2, L.HB_ORDER_ASC, C.byref(t), bits) == L.HB_ERR_EMPTY_WEIGHTS
+
+
+def test_try_from_bin_differential_on_random_bit_strings():
+    """HuffTree::try_from_bin (tree_inner.rs:522-604) on arbitrary input: the product's host parser and the oracle accept
+    and reject the same bit strings and, when they accept, read the same codes (duplicates, lone roots, deep chains)."""
+    rng = np.random.default_rng(2024)
+    accepted = rejected = 0
+    for it in range(600):
+        if it % 3 == 0:                                   # well-formed preorder strings of a random full binary tree
+            bits = []
+            pending = 1
+            leaves = 0
+            while pending:
+                pending -= 1
+                if leaves + pending < 200 and rng.random() < 0.48:
+                    bits.append(1)
+                    pending += 2
+                else:
+                    bits.append(0)
+                    bits.extend(int(b) for b in np.unpackbits(np.array([rng.integers(0, 256)], dtype=np.uint8)))
+                    leaves += 1
+            if rng.random() < 0.3:                        # truncate or extend some of them
+                cut = int(rng.integers(0, len(bits) + 1))
+                bits = bits[:cut] if rng.random() < 0.5 else bits + [int(b) for b in rng.integers(0, 2, size=cut % 17)]
+        else:
+            bits = [int(b) for b in rng.integers(0, 2, size=int(rng.integers(0, 400)))]
+        n_bits = len(bits)
+        raw = np.packbits(np.array(bits, dtype=np.uint8)) if n_bits else np.zeros(0, dtype=np.uint8)
+        try:
+            ref = O.tree_from_bin(raw, n_bits)
+        except O.OracleError:
+            ref = None
+        try:
+            ours = HuffTree.try_from_bin(raw.tobytes(), n_bits)
+        except FromBinError:
+            ours = None
+        assert (ours is None) == (ref is None), (it, n_bits)
+        if ours is not None:
+            accepted += 1
+            assert ours.read_codes() == ref.codes(), (it, n_bits)
+        else:
+            rejected += 1
+    assert accepted > 50 and rejected > 50

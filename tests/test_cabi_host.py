@@ -218,3 +218,45 @@ def test_try_from_bin_differential_on_random_bit_strings():
         else:
             rejected += 1
     assert accepted > 50 and rejected > 50
+
+
+def test_container_differential_on_random_blobs():
+    """CompressData::try_from_bytes (comp.rs:128-184) and to_bytes (:279-300): the product's host code and the oracle
+    classify random and mutated blobs alike and agree on (payload, padding, codes) when they accept."""
+    rng = np.random.default_rng(77)
+    t = HuffTree.from_weights({b: int(w) for b, w in zip(rng.choice(256, 40, replace=False), rng.integers(1, 1000, 40))})
+    good = CompressData(rng.integers(0, 256, size=50, dtype=np.uint8).tobytes(), 3, t).to_bytes()
+    agree_ok = agree_err = 0
+    for it in range(500):
+        if it % 2 == 0:
+            blob = bytearray(good)
+            for _ in range(int(rng.integers(1, 4))):
+                k = int(rng.integers(0, 4))
+                if k == 0 and len(blob) > 1:
+                    del blob[int(rng.integers(0, len(blob))):]
+                elif k == 1:
+                    blob[int(rng.integers(0, len(blob)))] ^= 1 << int(rng.integers(0, 8))
+                elif k == 2:
+                    blob[0:5] = bytes(rng.integers(0, 256, size=5, dtype=np.uint8))
+                else:
+                    blob += bytes(rng.integers(0, 256, size=int(rng.integers(1, 9)), dtype=np.uint8))
+            blob = bytes(blob)
+        else:
+            blob = bytes(rng.integers(0, 256, size=int(rng.integers(0, 64)), dtype=np.uint8))
+        try:
+            payload, pad, tree = O.try_from_bytes(np.frombuffer(blob, dtype=np.uint8))
+            ref = (payload.tobytes(), pad, tree.codes())
+        except O.OracleError:
+            ref = None
+        try:
+            cd = CompressData.try_from_bytes(blob)
+            ours = (cd.comp_bytes().tobytes(), cd.padding_bits(), cd.huff_tree().read_codes())
+        except (CompressedDataFromBytesError, HuffPanic):
+            ours = None
+        assert (ours is None) == (ref is None), (it, blob.hex())
+        if ours is not None:
+            assert ours == ref, (it, blob.hex())
+            agree_ok += 1
+        else:
+            agree_err += 1
+    assert agree_ok > 20 and agree_err > 20

@@ -13,7 +13,7 @@ workload = sys.argv[1] if len(sys.argv) > 1 else "uniform"
 size = int(sys.argv[2]) if len(sys.argv) > 2 else 256 << 20
 rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 eng = Engine(0)
-d = getattr(G, workload)(size, device=eng.device)
+d = (G.zipf(size, device=eng.device, s=(15, 10)) if workload == "zipf15" else getattr(G, workload)(size, device=eng.device))
 torch.cuda.synchronize()
 for r in range(rounds):
     out, n, pad, tree = eng.compress(d)

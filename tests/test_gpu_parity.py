@@ -178,6 +178,18 @@ def test_zipf_long_tail_codes_of_13_to_16_bits(hb, s):
     assert 12 < cd.huff_tree().raw.max_len <= 20
 
 
+def test_many_second_level_slots_take_the_global_table(hb):
+    # 5 geometric letters + 251 equally likely ones: 246 codes of 13 bits under 123 different depth-12 nodes -- more
+    # slots than the compact shared-memory copy of the second level holds, so the write pass reads it from global memory
+    p = np.zeros(256)
+    p[:5] = [0.5, 0.25, 0.125, 0.0625, 0.03125]
+    p[5:] = (1 - p[:5].sum()) / 251
+    data = np.random.default_rng(3).choice(np.arange(256, dtype=np.uint8), size=3_000_000, p=p)
+    cd = _assert_compress_parity(hb, data)
+    codes = cd.huff_tree().read_codes()
+    assert len({c[:12] for c in codes.values() if len(c) > 12}) > 96
+
+
 def test_geometric_tail_codes_in_all_three_decoder_levels(hb):
     # P(k) ~ 0.75^k over 64 letters: code lengths 2..~26, so the first-level table, the second-level table (13..20
     # bits) and the bit-serial walk (> 20 bits) are all hit, the first two often

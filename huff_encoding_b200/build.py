@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libhuffb200.so")
 SOURCES = ["hb_api.cu", "hb_tree.cpp"]
-HEADERS = ["hb_common.cuh", "hb_hist.cuh", "hb_encode.cuh", "hb_decode.cuh", os.path.join("..", "..", "include", "huffb200.h")]
+INCLUDE = os.path.join("..", "..", "include", "huffb200.h")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "--use_fast_math", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-shared", "-cudart", "static"]
@@ -22,7 +22,9 @@ def needs_build() -> bool:
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    # every source and header under csrc/ (a stale .so must never ship because a header was left off a list)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp", ".h", ".hpp"))]
+    deps += [os.path.join(CSRC, INCLUDE), os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

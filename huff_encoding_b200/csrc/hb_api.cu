@@ -15,6 +15,7 @@
 #include "hb_encode.cuh"
 #include "hb_fixed.cuh"
 #include "hb_hist.cuh"
+#include "hb_tables.cuh"
 
 namespace {
 
@@ -99,8 +100,10 @@ struct hb_ctx {
 
     // decoder
     hb::DecTables *d_dec_tables = nullptr;
+    uint32_t *d_emit = nullptr;          // multi-letter emit table of the fused decoder (1 << kEmitBitsMax entries)
     hb_tree dec_tree_cached;
-    bool dec_tree_valid = false;
+    bool dec_tree_valid = false;         // dec_tree_cached / dec_fixed_len describe the last tree seen
+    bool dec_tables_valid = false;       // d_dec_tables / d_emit were built for dec_tree_cached
     DevBuf<uint32_t> sub_info, blk_count, blk_local, dirty;
     DevBuf<uint64_t> blk_entry, blk_exit, group_total;
     DecResult *d_dec_result = nullptr;
@@ -209,20 +212,19 @@ hb_status launch_hist(hb_ctx *ctx, const uint8_t *d_data, size_t n, unsigned lon
 // ---------------------------------------------------------------- encoder
 hb_status upload_enc_table(hb_ctx *ctx, const hb_tree *tree) {
     if (ctx->enc_tree_valid && same_codes(ctx->enc_tree_cached, *tree)) return HB_OK;
-    hb::EncTable t;
-    std::memset(&t, 0, sizeof t);
+    // the code list travels as a kernel parameter; the table is built on the device (hb_tables.cuh)
+    hb::CodesParam cp;
     uint32_t max_len = 0;
     for (int b = 0; b < 256; b++) {
-        if (!tree->has_code[b]) continue;
-        const uint32_t len = tree->code_len[b];
-        if (len > HB_MAX_ENCODE_BITS) continue;            // such letters are rejected per input (check_encodable)
-        const uint64_t left = len ? tree->code[b] << (64 - len) : 0;       // code left-aligned in 64 bits
-        t.lo[b] = make_uint2(static_cast<uint32_t>(left >> 32), len);
-        t.hi[b] = static_cast<uint32_t>(left);
-        t.packed[b] = len <= 16 ? ((static_cast<uint32_t>(left >> 32) & 0xFFFF0000u) | len) : 0u;
+        uint32_t len = tree->has_code[b] ? tree->code_len[b] : 0;
+        if (len > HB_MAX_ENCODE_BITS) len = 0;             // such letters are rejected per input (check_encodable)
+        cp.len[b] = static_cast<uint8_t>(len);
+        cp.code[b] = len ? tree->code[b] : 0;
         max_len = std::max(max_len, len);
     }
-    HB_CUDA(cudaMemcpyAsync(ctx->d_enc_table, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream));
+    hb::enc_table_kernel<<<1, 256, 0, ctx->stream>>>(cp, ctx->d_enc_table);
+    ctx->launches++;
+    HB_CUDA(cudaGetLastError());
     ctx->enc_tree_cached = *tree;
     ctx->enc_tree_valid = true;
     ctx->enc_chunk = max_len <= 16 ? 4 : (max_len <= 32 ? 2 : 1);
@@ -243,6 +245,7 @@ hb_status launch_encode_s(hb_ctx *ctx, const uint8_t *d_data, size_t n, uint32_t
         HB_TRY(launch_hist(ctx, d_data, n, ctx->d_hist));
         if (!ctx->region_valid) return HB_ERR_INVALID_ARG;
     }
+    ctx->region_valid = false;        // consume-once: a different buffer may land on the same address later
     const int n_regions = static_cast<int>((n + ctx->region_letters - 1) / ctx->region_letters);
     hb::encode_regions_kernel<S><<<n_regions, hb::kEncThreads, hb::enc_smem_bytes(S), ctx->stream>>>(
         d_data, n, ctx->d_enc_table, start_bit, reinterpret_cast<uint32_t *>(d_out), ctx->d_region_hist,
@@ -297,86 +300,13 @@ hb_status check_encodable(const uint64_t weights[256], const hb_tree *tree, uint
 }
 
 // ---------------------------------------------------------------- decoder
-void build_dec_tables(const hb_tree *tree, hb::DecTables *t, int cnt_bits) {
-    std::memset(t, 0, sizeof *t);
-    auto leaf = [&](uint32_t n) { return tree->nodes[n].left == HB_NO_CHILD; };
-    for (uint32_t i = 0; i < tree->n_nodes && i < HB_MAX_NODES; i++) {
-        const hb_node &nd = tree->nodes[i];
-        t->nodes[i] = leaf(i) ? (0xFFFFu | (static_cast<uint32_t>(nd.letter) << 16))
-                              : (static_cast<uint32_t>(nd.left) | (static_cast<uint32_t>(nd.right) << 16));
-    }
-    const uint32_t root = tree->root;
-    t->root = root;
-    const int K = hb::kLutBits;
-    int n_slots = 0;
-    for (uint32_t p = 0; p < (1u << K); p++) {
-        if (leaf(root)) {
-            // comp.rs:496,506-509: a lone root emits its letter for every bit
-            t->lut[p] = static_cast<uint16_t>((1u << hb::kLutLenShift) | tree->nodes[root].letter);
-            continue;
-        }
-        // first code word
-        uint32_t node = root;
-        int used = 0;
-        while (used < K && !leaf(node)) {
-            const int bit = (p >> (K - 1 - used)) & 1;
-            node = bit ? tree->nodes[node].right : tree->nodes[node].left;
-            used++;
-        }
-        // short code: letter | len << 11 ; long code: long flag + the second-level slot of the depth-12 node
-        if (leaf(node)) {
-            t->lut[p] = static_cast<uint16_t>((static_cast<uint32_t>(used) << hb::kLutLenShift) | tree->nodes[node].letter);
-        } else {
-            int slot = -1;
-            for (int k = 0; k < n_slots; k++) if (t->slot_node[k] == node) { slot = k; break; }
-            if (slot < 0) {
-                slot = n_slots++;                          // at most 255 internal nodes exist, so slots never run out
-                t->slot_node[slot] = static_cast<uint16_t>(node);
-                for (uint32_t b8 = 0; b8 < 256; b8++) {    // stream bits 12..19 below this node
-                    uint32_t nd = node;
-                    int extra = 0;
-                    while (extra < 8 && !leaf(nd)) {
-                        nd = ((b8 >> (7 - extra)) & 1) ? tree->nodes[nd].right : tree->nodes[nd].left;
-                        extra++;
-                    }
-                    t->lut2[slot * 256 + b8] = leaf(nd)
-                        ? static_cast<uint16_t>((static_cast<uint32_t>(K + extra) << hb::kLutLenShift) | tree->nodes[nd].letter)
-                        : static_cast<uint16_t>(hb::kLutLongFlag | static_cast<uint32_t>(slot));
-                }
-            }
-            t->lut[p] = static_cast<uint16_t>(hb::kLutLongFlag | static_cast<uint32_t>(slot));
-        }
-    }
-    // multi-letter count table over CB bits: greedy run of complete code words
-    const int CB = cnt_bits;
-    for (uint32_t p = 0; p < (1u << CB); p++) {
-        if (leaf(root)) { t->cnt[p] = static_cast<uint8_t>((CB << 4) | CB); continue; }
-        int pos = 0, letters = 0;
-        for (;;) {
-            uint32_t nd = root;
-            int q = pos;
-            while (q < CB && !leaf(nd)) {
-                const int bit = (p >> (CB - 1 - q)) & 1;
-                nd = bit ? tree->nodes[nd].right : tree->nodes[nd].left;
-                q++;
-            }
-            if (!leaf(nd)) break;
-            pos = q;
-            letters++;
-            if (pos >= CB) break;
-        }
-        t->cnt[p] = static_cast<uint8_t>((pos << 4) | letters);
-    }
-}
-
-hb_status upload_dec_tables(hb_ctx *ctx, const hb_tree *tree) {
+// The decoder's view of a tree: remembers the last tree seen (fixed-length fast-path decision + its 256-byte table).
+// The big tables are NOT built here: only the general kernels need them (ensure_dec_tables).
+hb_status prepare_dec_tree(hb_ctx *ctx, const hb_tree *tree) {
     if (ctx->dec_tree_valid && same_nodes(ctx->dec_tree_cached, *tree)) return HB_OK;
-    static thread_local hb::DecTables t;
-    build_dec_tables(tree, &t, hb::kCntBits);
-    HB_CUDA(cudaMemcpyAsync(ctx->d_dec_tables, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream));
-    HB_CUDA(cudaStreamSynchronize(ctx->stream));       // `t` is reused by the next call
     ctx->dec_tree_cached = *tree;
     ctx->dec_tree_valid = true;
+    ctx->dec_tables_valid = false;
     ctx->dec_fixed_len = ctx->fastpath ? tree_fixed_len(tree) : 0;
     if (ctx->dec_fixed_len) {
         const uint32_t L = ctx->dec_fixed_len;
@@ -389,6 +319,29 @@ hb_status upload_dec_tables(hb_ctx *ctx, const hb_tree *tree) {
         }
         HB_CUDA(cudaMemcpyAsync(ctx->d_fix_dec, letters, sizeof letters, cudaMemcpyHostToDevice, ctx->stream));
     }
+    return HB_OK;
+}
+
+// Tables of the general decoder kernels for the tree of the last prepare_dec_tree call: one ~10 us kernel on the ctx
+// stream (hb_tables.cuh); the tree is its parameter.  No host-side table construction, no upload, no synchronisation.
+hb_status ensure_dec_tables(hb_ctx *ctx) {
+    if (ctx->dec_tables_valid) return HB_OK;
+    const hb_tree &tree = ctx->dec_tree_cached;
+    hb::TreeParam tp;
+    std::memset(&tp, 0, sizeof tp);
+    const uint32_t n = std::min<uint32_t>(tree.n_nodes, HB_MAX_NODES);
+    for (uint32_t i = 0; i < n; i++) {
+        const hb_node &nd = tree.nodes[i];
+        tp.nodes[i] = nd.left == HB_NO_CHILD ? (0xFFFFu | (static_cast<uint32_t>(nd.letter) << 16))
+                                             : (static_cast<uint32_t>(nd.left) | (static_cast<uint32_t>(nd.right) << 16));
+    }
+    tp.root = tree.root;
+    tp.n_nodes = n;
+    tp.emit_bits = 0;
+    hb::dec_tables_kernel<<<1, hb::kTabThreads, 0, ctx->stream>>>(tp, ctx->d_dec_tables, ctx->d_emit, hb::kCntBits);
+    ctx->launches++;
+    HB_CUDA(cudaGetLastError());
+    ctx->dec_tables_valid = true;
     return HB_OK;
 }
 
@@ -413,7 +366,7 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
         ctx->last_dec_valid = true;
         return HB_OK;
     }
-    HB_TRY(upload_dec_tables(ctx, tree));
+    HB_TRY(prepare_dec_tree(ctx, tree));
     ctx->last_dec_fixed = false;
     if (ctx->dec_fixed_len && entry_bit >= 0 && (entry_bit % 8) == 0 && static_cast<uint64_t>(entry_bit) >= own_begin) {
         // fixed-length code set: every L-th bit after the entry starts a code word; nothing to count on the device
@@ -432,6 +385,7 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
         ctx->last_dec_valid = true;
         return HB_OK;
     }
+    HB_TRY(ensure_dec_tables(ctx));
     const uint64_t chunk_bits = static_cast<uint64_t>(hb::kChunkWords) * 32;
     const uint64_t first_block = own_begin / chunk_bits;
     const uint64_t last_block = (own_end - 1) / chunk_bits;
@@ -600,6 +554,7 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
         HB_CUDA(cudaMalloc(&ctx->d_enc_table, sizeof(hb::EncTable)));
         HB_CUDA(cudaMalloc(&ctx->d_total_bits, sizeof(unsigned long long)));
         HB_CUDA(cudaMalloc(&ctx->d_dec_tables, sizeof(hb::DecTables)));
+        HB_CUDA(cudaMalloc(&ctx->d_emit, sizeof(uint32_t) << 13));
         HB_CUDA(cudaMalloc(&ctx->d_fix_enc, 256));
         HB_CUDA(cudaMalloc(&ctx->d_fix_dec, 256));
         { const char *nf = std::getenv("HB_NO_FASTPATH"); ctx->fastpath = !(nf && nf[0] == '1'); }
@@ -640,7 +595,7 @@ hb_status hb_ctx_destroy(hb_ctx *ctx) {
     struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_hist); cudaFree(ctx->d_region_hist); cudaFree(ctx->d_enc_table); cudaFree(ctx->d_total_bits); cudaFree(ctx->d_dec_tables); cudaFree(ctx->d_fix_enc); cudaFree(ctx->d_fix_dec);
+    cudaFree(ctx->d_hist); cudaFree(ctx->d_region_hist); cudaFree(ctx->d_enc_table); cudaFree(ctx->d_total_bits); cudaFree(ctx->d_dec_tables); cudaFree(ctx->d_emit); cudaFree(ctx->d_fix_enc); cudaFree(ctx->d_fix_dec);
     cudaFree(ctx->d_dec_result); cudaFree(ctx->d_n_dirty);
     if (ctx->h_dec_result) cudaFreeHost(ctx->h_dec_result);
     if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
@@ -880,7 +835,7 @@ static hb_status decompress_host_common(hb_ctx *ctx, const uint8_t *comp, size_t
     if (padding_bits > 7) return HB_ERR_BAD_PADDING;
     if (!comp) return HB_ERR_INVALID_ARG;
     const uint64_t total_bits = static_cast<uint64_t>(comp_len) * 8 - padding_bits;
-    HB_TRY(upload_dec_tables(ctx, tree));
+    HB_TRY(prepare_dec_tree(ctx, tree));
     if (ctx->dec_fixed_len) {
         const size_t n = static_cast<size_t>(total_bits / ctx->dec_fixed_len);   // trailing bits that complete no code are dropped
         if (dst && n > cap) { *out_n = n; return HB_ERR_CAPACITY; }

@@ -325,8 +325,16 @@ __device__ __forceinline__ void dec_load_window(const DecParams &p, uint32_t chu
             const int i4 = threadIdx.x + k * kDecThreads;
             const long long gw = w_begin + 4ll * i4;
             v[k] = make_uint4(0, 0, 0, 0);
-            if (i4 < kVecs && gw >= 0 && static_cast<uint64_t>(gw) < p.n_words_readable)
-                v[k] = ld_stream_u4(reinterpret_cast<const uint4 *>(p.words + gw));
+            if (i4 < kVecs && gw >= 0 && static_cast<uint64_t>(gw) < p.n_words_readable) {
+                if (static_cast<uint64_t>(gw) + 4 <= p.n_words_readable) {
+                    v[k] = ld_stream_u4(reinterpret_cast<const uint4 *>(p.words + gw));
+                } else {                       // last vector of the stream: never read past the last stream word
+                    const uint64_t left = p.n_words_readable - static_cast<uint64_t>(gw);
+                    v[k].x = ld_stream_u32(p.words + gw);
+                    if (left > 1) v[k].y = ld_stream_u32(p.words + gw + 1);
+                    if (left > 2) v[k].z = ld_stream_u32(p.words + gw + 2);
+                }
+            }
         }
 #pragma unroll
         for (int k = 0; k < kPerThread; k++) {

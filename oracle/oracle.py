@@ -179,12 +179,19 @@ def compress(data, order: int = ORDER_ASC) -> tuple[np.ndarray, int, HoTree]:
 
 
 def decompress(comp, padding_bits: int, tree: HoTree) -> np.ndarray:
+    """One bit-serial walk (comp.rs:487-519).  The reference grows a Vec (comp.rs:491); here the output is sized for
+    the worst case up front (every letter = the tree's shortest code), which costs no time: untouched pages are never
+    committed."""
     a = _as_u8(comp)
+    if a.size == 0 or padding_bits > 7:
+        n0 = C.c_size_t(0)
+        raise OracleError(lib().ho_decompress_count(a.ctypes.data if a.size else None, a.size, padding_bits,
+                                                    C.byref(tree), C.byref(n0)) or ERR_EMPTY_COMP)
+    lens = [tree.code_len[b] for b in range(256) if tree.has_code[b]]
+    shortest = max(1, min(lens)) if lens else 1
+    cap = (a.size * 8 - padding_bits) // shortest + 1
+    out = np.empty(cap, dtype=np.uint8)
     n = C.c_size_t(0)
-    rc = lib().ho_decompress_count(a.ctypes.data, a.size, padding_bits, C.byref(tree), C.byref(n))
-    if rc:
-        raise OracleError(rc)
-    out = np.empty(max(n.value, 1), dtype=np.uint8)
     rc = lib().ho_decompress(a.ctypes.data, a.size, padding_bits, C.byref(tree), out.ctypes.data, out.size, C.byref(n))
     if rc:
         raise OracleError(rc)

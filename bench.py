@@ -136,17 +136,39 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------- workloads
-def make_workload(name: str, n: int, offset: int, device):
+WORKLOADS = ("uniform", "zipf", "english", "zipf15", "zipf20", "fibonacci")
+CONFIG_NAME = {"uniform": "BASELINE.json configs[1]: uniform random bytes", "zipf": "BASELINE.json configs[2]: Zipf(1.2) bytes",
+               "english": "BASELINE.json configs[3]: English-like text", "fibonacci": "BASELINE.json configs[4]: Fibonacci-256 runs",
+               "zipf15": "Zipf(1.5) bytes (codes up to 14 bits)", "zipf20": "Zipf(2.0) bytes"}
+
+
+def make_workload(name: str, n: int, offset: int, device, seed_shift: int = 0):
+    """seed_shift != 0 gives a second input of the same distribution with different counts (hence a different tree)."""
     from huff_encoding_b200 import datagen as G
-    gen = {"uniform": G.uniform, "zipf": G.zipf, "english": G.english,
-           "zipf15": lambda *a, **k: G.zipf(*a, s=(15, 10), **k), "zipf20": lambda *a, **k: G.zipf(*a, s=(20, 10), **k)}[name]
-    return gen(n, offset=offset, device=device)
+    if name == "fibonacci":
+        return G.from_weights_runs(G.fibonacci_weights(), device=device)
+    base = {"uniform": G.SEED_BASE + 1, "zipf": G.SEED_BASE + 2, "english": G.SEED_BASE + 0,
+            "zipf15": G.SEED_BASE + 2, "zipf20": G.SEED_BASE + 2}[name]
+    kw = {"seed": base + 1000 * seed_shift, "offset": offset, "device": device}
+    if name == "zipf15":
+        return G.zipf(n, s=(15, 10), **kw)
+    if name == "zipf20":
+        return G.zipf(n, s=(20, 10), **kw)
+    return {"uniform": G.uniform, "zipf": G.zipf, "english": G.english}[name](n, **kw)
+
+
+def make_config(args, world: int) -> dict:
+    """The SAME dict in both arms (ours / reference): what the metric is quoted on."""
+    return {"workload": f"{CONFIG_NAME[args.workload]}, {args.size} B per GPU, weak scaling over contiguous shards; "
+                        "the CPU reference arm times a bounded prefix of the same generator per step (cpu_baseline.sample)",
+            "bytes_per_gpu": args.size, "inputs_rotated_per_step": 2,
+            "l2": "input per step >> 126 MB L2", "parallelism": f"contiguous shards x{world}" if world > 1 else "single GPU"}
 
 
 def cpu_port_round_trip(name: str, sample_bytes: int, repeats: int = 1):
     """The oracle's C port of the reference algorithm (single thread, like the reference's own loops,
-    comp.rs:424-444 and :513-516) on a bounded sample of the workload.  Returns GB/s of input for
-    compress + decompress."""
+    comp.rs:424-444 and :513-516) on a bounded sample of the workload: compress (count + tree + per-bit packing) and
+    decompress (ONE bit-serial walk).  Returns (GB/s of input for compress + decompress, seconds, split)."""
     import numpy as np
     from oracle import oracle as O
     data = make_workload(name, sample_bytes, 0, None)
@@ -155,41 +177,42 @@ def cpu_port_round_trip(name: str, sample_bytes: int, repeats: int = 1):
     for _ in range(repeats):
         t0 = time.perf_counter()
         comp, pad, tree = O.compress(data)
+        t1 = time.perf_counter()
         out = O.decompress(comp, pad, tree)
-        dt = time.perf_counter() - t0
+        t2 = time.perf_counter()
         assert out.size == data.size and np.array_equal(out[:4096], data[:4096])
-        best = dt if best is None else min(best, dt)
-    return sample_bytes / best / 1e9, best
+        if best is None or t2 - t0 < best[0]:
+            best = (t2 - t0, t1 - t0, t2 - t1)
+    return data.size / best[0] / 1e9, best[0], {"compress_gbs": data.size / best[1] / 1e9, "decompress_gbs": data.size / best[2] / 1e9}
 
 
 # ---------------------------------------------------------------- reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
     # bounded sample: calibrate on 4 MiB, then size the per-step sample so that K steps take ~100 s in total
-    rate, _ = cpu_port_round_trip(args.workload, 4 << 20)                     # GB/s
+    rate, _, _ = cpu_port_round_trip(args.workload, 4 << 20)                     # GB/s
     budget = int(rate * 1e9 * 100.0 / max(args.steps, 1))
     sample = max(1 << 20, min(args.size, 64 << 20, budget)) // (1 << 20) * (1 << 20)
-    vals = []
     for _ in range(args.warmup):
         cpu_port_round_trip(args.workload, min(sample, 2 << 20))
-    t_all = 0.0
+    t_all, split = 0.0, None
     for _ in range(args.steps):
-        v, dt = cpu_port_round_trip(args.workload, sample)
-        vals.append(v)
+        _, dt, split = cpu_port_round_trip(args.workload, sample)
         t_all += dt
     value = sample * args.steps / t_all / 1e9
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_all / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{args.workload} random bytes, {args.size} B per GPU (BASELINE.json configs[1])",
-                   "bytes_per_gpu": args.size},
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": make_config(args, world),
+        "sample_bytes_per_step": sample,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": f"first {sample} B of the workload per step; C port of the reference algorithm "
                                    "(oracle/huff_oracle.c), single thread like the reference's compress/decompress "
-                                   "loops; the Rust crate itself cannot be built here (no rustc/cargo)"},
+                                   "loops, one bit-serial decode walk; the Rust crate itself cannot be built here "
+                                   "(no rustc/cargo)", "split_last_step": split},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -198,6 +221,91 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------- our arm
+PHASES = ("hist", "encode", "decode")
+
+
+def _frac(bytes_, ms, peak):
+    return round(bytes_ / (ms * 1e-3) / 1e9 / peak, 4) if ms and ms > 0 else None
+
+
+def measure(codec, eng, datas, comp_buf, out_buf, steps, warmup, torch, dist, world, peak):
+    """Device-resident round trips over the inputs in `datas`, rotated step by step (so every step meets a tree the
+    context did not see in the previous step).  Returns timing + per-phase CUDA-event breakdown + parity check."""
+    stream = eng.stream
+    with torch.cuda.stream(stream):
+        for i in range(warmup):
+            codec.round_trip(datas[i % len(datas)], comp_buf, out_buf)
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for i in range(steps):
+            codec.round_trip(datas[i % len(datas)], comp_buf, out_buf)
+        ev1.record(stream)
+        stream.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        total_ms = ev0.elapsed_time(ev1)
+        last = datas[(steps - 1) % len(datas)]
+        n = last.numel()
+        assert codec.last_info["n_letters"] == n and torch.equal(out_buf[:n], last), "round trip mismatch"
+        # per-phase breakdown: extra steps with CUDA events between the phases (not part of the timing above)
+        k = min(max(steps, 2), 6)
+        marks = [codec.round_trip(datas[i % len(datas)], comp_buf, out_buf, want_events=True) for i in range(k)]
+        stream.synchronize()
+    phase = {ph: sum(m[ph][0].elapsed_time(m[ph][1]) for m in marks) / len(marks) for ph in PHASES}
+    t = torch.tensor([total_ms] + [phase[ph] for ph in PHASES], dtype=torch.float64, device=last.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t[0])
+    phase = {ph: float(t[1 + i]) for i, ph in enumerate(PHASES)}
+    info = codec.last_info
+    c = info["comp_len"]
+    ms = total_ms / steps
+    comp_ms, dec_ms = phase["hist"] + phase["encode"], phase["decode"]
+    res = {"bytes_per_gpu": n, "comp_bytes_per_gpu": c, "ms_per_step": round(ms, 4),
+           "round_trip_gbs": round(n * world / (ms * 1e-3) / 1e9, 1),
+           "compress_gbs": round(n * world / (comp_ms * 1e-3) / 1e9, 1),
+           "decompress_gbs": round(n * world / (dec_ms * 1e-3) / 1e9, 1),
+           "phase_ms": {ph: round(v, 4) for ph, v in phase.items()},
+           "frac": {"hist": _frac(n, phase["hist"], peak), "encode": _frac(n + c, phase["encode"], peak),
+                    "decode": _frac(n + c, phase["decode"], peak), "compress": _frac(2 * n + c, comp_ms, peak)},
+           "decoder": {0: "fixed-length translation" if info.get("fixed_len") else "two-pass (count + write)",
+                       1: "fused one-pass", 2: "fused refuted -> two-pass"}.get(eng.ctx.last_decode_path()[0], "?")}
+    return res
+
+
+def e2e_round_trip(api, eng, data, steps, torch, dist, world, np):
+    """The host-buffer C ABI (hb_compress_u8_into + hb_decompress_u8_into) with pinned HOST buffers: every step copies
+    the letters H2D, the stream D2H, the stream H2D and the letters D2H inside the timed region."""
+    n = data.numel()
+    host_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    host_in.copy_(data)
+    host_comp = torch.empty(n + n // 8 + 4096, dtype=torch.uint8, pin_memory=True)
+    host_out = torch.empty(n + 64, dtype=torch.uint8, pin_memory=True)
+    h_np, c_np, o_np = host_in.numpy(), host_comp.numpy(), host_out.numpy()
+    cd = api.compress(h_np, ctx=eng.ctx, out=c_np)          # warm-up (device staging buffers)
+    _ = api.decompress(cd, ctx=eng.ctx, out=o_np)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cd = api.compress(h_np, ctx=eng.ctx, out=c_np)
+        back = api.decompress(cd, ctx=eng.ctx, out=o_np)
+    dt = (time.perf_counter() - t0) / steps
+    assert back.size == n and np.array_equal(back[:65536], h_np[:65536]) and np.array_equal(back[-4096:], h_np[-4096:])
+    clen = int(cd.comp_bytes().size)
+    t = torch.tensor([dt], dtype=torch.float64, device=data.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"value": n * world / float(t.item()) / 1e9, "unit": UNIT, "h2d_bytes_per_step": n + clen,
+            "d2h_bytes_per_step": clen + n, "steps": steps,
+            "api": "hb_compress_u8_into + hb_decompress_u8_into (pinned host buffers in and out)"}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -218,226 +326,134 @@ def run_ours(args):
         build.build()
     if world > 1:
         dist.barrier()
+    from huff_encoding_b200 import api
     from huff_encoding_b200.engine import Engine
     from huff_encoding_b200.sharded import ShardedCodec
 
+    peak, peak_src = measured_peak_gbs()
     eng = Engine(local_rank)
     codec = ShardedCodec(eng, world, rank, dist if world > 1 else None)
     n = args.size
-    data = make_workload(args.workload, n, rank * n, dev)
+    d = dist if world > 1 else None
+
+    def buffers(nbytes):
+        return (torch.empty(nbytes + nbytes // 4 + 4096, dtype=torch.uint8, device=dev),
+                torch.empty(nbytes + 64, dtype=torch.uint8, device=dev))
+
+    # ---- headline: BASELINE.json configs[1] (or --workload), two inputs of the same shape rotated step by step: every
+    #      compress() builds a tree from a fresh histogram and every decompress() meets a tree it did not see last step
+    datas = [make_workload(args.workload, n, rank * n, dev, seed_shift=k) for k in range(2)]
+    comp_buf, out_buf = buffers(max(x.numel() for x in datas))
     torch.cuda.synchronize()
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local_rank, uuid)
+    sampler.start()
+    time.sleep(0.05)
+    # warm caches first (same input every step), then the timed, rotating run
+    warm = measure(codec, eng, datas[:1], comp_buf, out_buf, max(3, args.steps // 2), args.warmup, torch, d, world, peak)
+    sampler.clear()
+    launches0 = eng.kernel_launches()
+    head = measure(codec, eng, datas, comp_buf, out_buf, args.steps, args.warmup, torch, d, world, peak)
+    clocks = sampler.stop()
+    # measure() runs warm-up + timed + up to 6 event-instrumented steps: count the launches of the timed steps only
+    per_step = (eng.kernel_launches() - launches0) / (args.warmup + args.steps + min(max(args.steps, 2), 6))
+    launches = int(round(per_step * args.steps))
+    e2e = e2e_round_trip(api, eng, datas[0], max(1, min(args.steps, 4)), torch, d, world, np)
+    cpu = None
+    if world == 1 and rank == 0:
+        sample = min(n, 128 << 20)
+        cpu_v, cpu_dt, cpu_split = cpu_port_round_trip(args.workload, sample)
+        cpu = {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"first {sample} B of the workload, compress+decompress once ({cpu_dt:.1f} s); C port of the "
+                         "reference algorithm, single thread, one bit-serial decode walk", "split": cpu_split}
+    del datas
 
-    comp_buf = torch.empty(n + n // 4 + 4096, dtype=torch.uint8, device=dev)
-    out_buf = torch.empty(n + 64, dtype=torch.uint8, device=dev)
-    stream = eng.stream
-    phases = ["hist", "encode", "dec_count", "dec_write"]
-    phase_ms = {k: 0.0 for k in phases}
+    # ---- the other BASELINE configs on the same GPUs: the variable-length (real Huffman) kernels
+    configs = []
+    if not args.no_general:
+        def run_config(label, workload, nbytes, scaling, steps=3, with_e2e=False):
+            ds = [make_workload(workload, nbytes, rank * nbytes, dev, seed_shift=k) for k in range(1 if workload == "fibonacci" else 2)]
+            cb, ob = buffers(max(x.numel() for x in ds))
+            r = measure(codec, eng, ds, cb, ob, steps, 2, torch, d, world, peak)
+            r.update({"config": label, "workload": workload, "n_gpus": world, "scaling": scaling})
+            if with_e2e:
+                r["e2e"] = e2e_round_trip(api, eng, ds[0], 2, torch, d, world, np)
+            configs.append(r)
+            del ds, cb, ob
+            torch.cuda.empty_cache()
 
-    def step(record: bool):
-        marks = codec.round_trip(data, comp_buf, out_buf, want_events=record)
-        return marks
+        run_config("1 GiB Zipf(1.2) per GPU (north_star: 1-GPU encode and decode on 1 GiB inputs)", "zipf", 1 << 30, "weak",
+                   steps=5, with_e2e=True)
+        if world == 1:
+            run_config("configs[2]: 4 GiB Zipf(1.2) on one GPU", "zipf", 4 << 30, "weak")
+            run_config("configs[4]: Fibonacci-256, 1 836 311 750 B, 40-bit codes", "fibonacci", 0, "weak", steps=2)
+            run_config("Zipf(1.5), 1 GiB: 1.5 % of the letters have codes beyond the 12-bit tables", "zipf15", 1 << 30, "weak")
+        else:
+            run_config(f"configs[2] weak: 4 GiB Zipf(1.2) per GPU x{world}", "zipf", 4 << 30, "weak")
+            run_config(f"configs[2] strong: 4 GiB Zipf(1.2) in total over {world} GPUs", "zipf", (4 << 30) // world, "strong")
+        run_config(f"configs[3]: English-like text, 2 GiB contiguous shard per GPU x{world}", "english", 2 << 30, "weak")
 
-    with torch.cuda.stream(stream):
-        try:
-            uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
-        except Exception:
-            uuid = None
-        sampler = ClockSampler(local_rank, uuid)
-        sampler.start()
-        time.sleep(0.05)
-        for _ in range(args.warmup):
-            step(False)
-        stream.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        sampler.clear()                      # keep only samples taken during the timed region
-        launches0 = eng.kernel_launches()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        for _ in range(args.steps):
-            step(False)                       # the timed region: no per-phase events, nothing but the product path
-        ev1.record(stream)
-        stream.synchronize()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        clocks = sampler.stop()
-        launches = eng.kernel_launches() - launches0
-        # per-kernel breakdown: a few extra steps with CUDA events between the phases (not part of `value`)
-        all_marks = [codec.round_trip(data, comp_buf, out_buf, want_events=True) for _ in range(min(args.steps, 10))]
-        stream.synchronize()
-    total_ms = ev0.elapsed_time(ev1)
-    for marks in all_marks:
-        for k in phases:
-            a, b = marks[k]
-            phase_ms[k] += a.elapsed_time(b)
-    for k in phases:
-        phase_ms[k] /= len(all_marks)
-    info = codec.last_info
-
-    # correctness of what was timed (not in the timed region): round trip restores the shard
-    assert info["n_letters"] == n and torch.equal(out_buf[:n], data), "round trip mismatch"
-
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = n * world / (ms_per_step * 1e-3) / 1e9
-
-    # ---- secondary measurement: the GENERAL path (variable-length codes) on Zipf(1.2) bytes of the same size.
-    # configs[1] (uniform) yields a fixed-length code set and takes the table-translation fast path; this shows what
-    # the scan / self-synchronising kernels do.  Not part of `value`.
-    general = None
-    if args.workload == "uniform" and not args.no_general:
-        zdata = make_workload("zipf", n, rank * n, dev)
-        gphase = {k: 0.0 for k in phases}
-        gsteps = 3
-        with torch.cuda.stream(stream):
-            for _ in range(2):
-                codec.round_trip(zdata, comp_buf, out_buf)
-            stream.synchronize()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record(stream)
-            gm = [codec.round_trip(zdata, comp_buf, out_buf, want_events=True) for _ in range(gsteps)]
-            g1.record(stream)
-            stream.synchronize()
-        assert torch.equal(out_buf[:n], zdata), "general-path round trip mismatch"
-        for m in gm:
-            for k in phases:
-                gphase[k] += m[k][0].elapsed_time(m[k][1]) / gsteps
-        zc = codec.last_info["comp_len"]
-        general = {"workload": f"zipf(1.2) bytes, {n} B per GPU", "ms_per_step": g0.elapsed_time(g1) / gsteps,
-                   "comp_bytes": zc, "phase_ms": {k: round(v, 4) for k, v in gphase.items()},
-                   "alg_bytes": {"hist": n, "encode": n + zc, "dec_count": zc, "dec_write": zc + n}}
-        del zdata
-        # a long-tailed input (Zipf(1.5): codes up to 14 bits, 1.5 % of the letters beyond the 12-bit decode table):
-        # the decoder instances for trees with long codes
-        ldata = make_workload("zipf15", n, rank * n, dev)
-        lphase = {k: 0.0 for k in phases}
-        with torch.cuda.stream(stream):
-            for _ in range(2):
-                codec.round_trip(ldata, comp_buf, out_buf)
-            stream.synchronize()
-            lm = [codec.round_trip(ldata, comp_buf, out_buf, want_events=True) for _ in range(gsteps)]
-            stream.synchronize()
-        assert torch.equal(out_buf[:n], ldata), "long-code round trip mismatch"
-        for m in lm:
-            for k in phases:
-                lphase[k] += m[k][0].elapsed_time(m[k][1]) / gsteps
-        general["zipf15_long_codes_phase_ms"] = {k: round(v, 4) for k, v in lphase.items()}
-        del ldata
-        # the same uniform input forced through the general kernels (fast path off): what configs[1] costs without it
-        os.environ["HB_NO_FASTPATH"] = "1"
-        try:
-            eng2 = Engine(local_rank)
-        finally:
-            del os.environ["HB_NO_FASTPATH"]
-        codec2 = ShardedCodec(eng2, world, rank, dist if world > 1 else None)
-        uphase = {k: 0.0 for k in phases}
-        with torch.cuda.stream(eng2.stream):
-            for _ in range(2):
-                codec2.round_trip(data, comp_buf, out_buf, want_events=True)
-            eng2.stream.synchronize()
-            um = [codec2.round_trip(data, comp_buf, out_buf, want_events=True) for _ in range(gsteps)]
-            eng2.stream.synchronize()
-        assert torch.equal(out_buf[:n], data), "forced general-path round trip mismatch"
-        for m in um:
-            for k in phases:
-                uphase[k] += m[k][0].elapsed_time(m[k][1]) / gsteps
-        general["uniform_forced_general_phase_ms"] = {k: round(v, 4) for k, v in uphase.items()}
-        del codec2, eng2
-        codec.round_trip(data, comp_buf, out_buf)      # restore last_info for the headline workload
-        info = codec.last_info
-
-    # ---- e2e through the host-buffer C ABI with pinned host memory
-    from huff_encoding_b200 import api
-    e2e_n = n
-    host_in = torch.empty(e2e_n, dtype=torch.uint8, pin_memory=True)
-    host_in.copy_(data[:e2e_n])
-    host_comp = torch.empty(e2e_n + e2e_n // 8 + 4096, dtype=torch.uint8, pin_memory=True)
-    host_out = torch.empty(e2e_n + 64, dtype=torch.uint8, pin_memory=True)
-    h_np, c_np, o_np = host_in.numpy(), host_comp.numpy(), host_out.numpy()
-    e2e_steps = max(1, min(args.steps, 5))
-    cd = api.compress(h_np, ctx=eng.ctx, out=c_np)          # warm-up (device staging buffers, tables)
-    _ = api.decompress(cd, ctx=eng.ctx, out=o_np)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        cd = api.compress(h_np, ctx=eng.ctx, out=c_np)      # H2D of the letters + D2H of the stream inside
-        back = api.decompress(cd, ctx=eng.ctx, out=o_np)    # H2D of the stream + D2H of the letters inside
-    e2e_dt = (time.perf_counter() - t0) / e2e_steps
-    assert back.size == e2e_n and np.array_equal(back[:65536], h_np[:65536]) and np.array_equal(back[-4096:], h_np[-4096:])
-    clen = int(cd.comp_bytes().size)
-    t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = e2e_n * world / float(t.item()) / 1e9
+        # bit-exactness of the sharded path (outside every timed region): the gathered shard streams must equal the
+        # stream ONE GPU produces for the concatenated input
+        m = 32 << 20
+        part = make_workload("english", m, rank * m, dev)
+        cb, ob = buffers(m)
+        info = codec.compress(part, cb)
+        got = codec.gather_stream(cb, info)
+        parts = [torch.empty_like(part) for _ in range(world)] if rank == 0 else None
+        dist.gather(part, parts, dst=0)
+        if rank == 0:
+            whole = torch.cat(parts)
+            out1, clen1, pad1, _ = Engine.compress(eng, whole)
+            assert got[1] == pad1 and got[0].size == clen1 and np.array_equal(got[0], out1[:clen1].cpu().numpy()), \
+                "concatenated shard streams differ from the single-GPU stream"
+        sharded_check = "gathered shard streams == single-GPU stream of the concatenated input (32 MiB per rank): ok"
+    else:
+        sharded_check = None
 
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        c_bytes = info["comp_len"]
-        algo = {"hist": n, "encode": n + c_bytes, "dec_count": c_bytes, "dec_write": c_bytes + n}
-        kern = {}
-        fixed = info.get("fixed_len", 0)
-        for k in phases:
-            ms = phase_ms[k]
-            host_only = (k == "dec_count" and fixed)    # fixed-length code set: the count is host arithmetic, no kernel
-            kern[k] = {"ms": round(ms, 4), "algorithmic_bytes": 0 if host_only else algo[k],
-                       "achieved_gbs": round(algo[k] / (ms * 1e-3) / 1e9, 1) if ms > 0 and not host_only else None,
-                       "frac": round(algo[k] / (ms * 1e-3) / 1e9 / peak, 4) if ms > 0 and not host_only else None}
-            if host_only:
-                kern[k]["note"] = "no kernel: fixed-length code set, letter count = bits / L on the host"
-        # the dominant kernel = the largest share of the step; decode is reported as count+write against C+N
-        dom = max([k for k in phases if kern[k]["frac"] is not None], key=lambda k: phase_ms[k])
-        dec_ms = phase_ms["dec_count"] + phase_ms["dec_write"]
-        comp_ms = phase_ms["hist"] + phase_ms["encode"]
+        phase = head["phase_ms"]
+        c_bytes = head["comp_bytes_per_gpu"]
+        algo = {"hist": n, "encode": n + c_bytes, "decode": c_bytes + n}
+        kern = {k: {"ms": phase[k], "algorithmic_bytes": algo[k],
+                    "achieved_gbs": round(algo[k] / (phase[k] * 1e-3) / 1e9, 1) if phase[k] > 0 else None,
+                    "frac": _frac(algo[k], phase[k], peak)} for k in PHASES}
+        dom = max(PHASES, key=lambda k: phase[k])
         traffic, traffic_src = None, None
         try:                                              # measured DRAM bytes per launch from the committed ncu capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             traffic = tj.get(f"{args.workload}:{n}", {}).get(dom)
             traffic_src = tj.get("_source") if traffic is not None else None
         except Exception:
             pass
+        comp_ms = phase["hist"] + phase["encode"]
         roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kern[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernels": kern,
-                "compress": {"ms": round(comp_ms, 4), "algorithmic_bytes": 2 * n + c_bytes,
-                             "frac": round((2 * n + c_bytes) / (comp_ms * 1e-3) / 1e9 / peak, 4)},
-                "decompress": {"ms": round(dec_ms, 4), "algorithmic_bytes": n + c_bytes,
-                               "frac": round((n + c_bytes) / (dec_ms * 1e-3) / 1e9 / peak, 4)}}
-        sample = min(n, 128 << 20)
-        cpu_v, cpu_dt = cpu_port_round_trip(args.workload, sample) if world == 1 else (None, None)
+                "compress": {"ms": round(comp_ms, 4), "algorithmic_bytes": 2 * n + c_bytes, "frac": _frac(2 * n + c_bytes, comp_ms, peak)},
+                "decompress": {"ms": phase["decode"], "algorithmic_bytes": n + c_bytes, "frac": _frac(n + c_bytes, phase["decode"], peak)}}
+        cfg = make_config(args, world)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"{args.workload} random bytes, {n} B per GPU (BASELINE.json configs[1])",
-                       "bytes_per_gpu": n, "comp_bytes_per_gpu": c_bytes, "l2": "input per step >> 126 MB L2",
-                       "parallelism": f"contiguous shards x{world}" if world > 1 else "single GPU"},
-            "compress_gbs": n * world / (comp_ms * 1e-3) / 1e9, "decompress_gbs": n * world / (dec_ms * 1e-3) / 1e9,
-            "roofline": roof,
-            "cpu_baseline": ({"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",
-                              "sample": f"first {sample} B of the workload, compress+decompress once "
-                                        f"({cpu_dt:.1f} s); C port of the reference algorithm, single thread"}
-                             if cpu_v is not None else None),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_n + clen,
-                    "d2h_bytes_per_step": clen + e2e_n, "steps": e2e_steps,
-                    "api": "hb_compress_u8_into + hb_decompress_u8_into (pinned host buffers in and out)"},
-            "gpu_launches": launches, "clocks": clocks,
+            "metric": METRIC, "value": n * world / (head["ms_per_step"] * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
+            "comp_bytes_per_gpu": c_bytes,
+            "cold_tree_ms_per_step": head["ms_per_step"], "warm_tree_ms_per_step": warm["ms_per_step"],
+            "compress_gbs": head["compress_gbs"], "decompress_gbs": head["decompress_gbs"], "decoder": head["decoder"],
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
-        if general is not None:
-            gp = general["phase_ms"]
-            ga = general["alg_bytes"]
-            general["frac"] = {k: round(ga[k] / (gp[k] * 1e-3) / 1e9 / peak, 4) if gp[k] > 0 else None for k in gp}
-            cms, dms = gp["hist"] + gp["encode"], gp["dec_count"] + gp["dec_write"]
-            general["compress_gbs"] = n * world / (cms * 1e-3) / 1e9
-            general["decompress_gbs"] = n * world / (dms * 1e-3) / 1e9
-            general["compress_frac"] = round((2 * n + general["comp_bytes"]) / (cms * 1e-3) / 1e9 / peak, 4)
-            general["decompress_frac"] = round((n + general["comp_bytes"]) / (dms * 1e-3) / 1e9 / peak, 4)
-            line["general_path"] = general
+        gen = [c for c in configs if c["workload"] == "zipf" and c["bytes_per_gpu"] == (1 << 30)]
+        if gen:
+            line["general_frac"] = {"encode": gen[0]["frac"]["encode"], "decode": gen[0]["frac"]["decode"],
+                                    "compress": gen[0]["frac"]["compress"], "workload": gen[0]["config"]}
+        if configs:
+            line["configs"] = configs
+        if sharded_check:
+            line["sharded_parity"] = sharded_check
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -450,9 +466,9 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="uniform", choices=["uniform", "zipf", "english", "zipf15", "zipf20"])
+    ap.add_argument("--workload", default="uniform", choices=list(WORKLOADS))
     ap.add_argument("--size", type=int, default=1 << 30, help="bytes per GPU")
-    ap.add_argument("--no-general", action="store_true", help="skip the secondary general-path (zipf) measurement")
+    ap.add_argument("--no-general", action="store_true", help="skip the secondary configs (zipf / text / fibonacci)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -95,6 +95,9 @@ SYMBOLS = [
     ("hb_decode_count_dev", C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _treep,
                                       C.POINTER(HbShardInfo)]),
     ("hb_decode_write_dev", C.c_int, [_vp, _vp, C.c_size_t]),
+    ("hb_decode_shard_dev", C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _treep,
+                                      C.POINTER(HbShardInfo), _vp, C.c_size_t]),
+    ("hb_ctx_last_decode_path", C.c_int, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
 ]
 
 _lib = None

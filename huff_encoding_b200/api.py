@@ -132,6 +132,13 @@ class Context:
         _raise(self._lib.hb_ctx_last_decode_repairs(self._h, C.byref(n)))
         return n.value
 
+    def last_decode_path(self) -> tuple[int, int]:
+        """(path, slow_chunks) of the last decompress: path 0 = two-pass / fixed-length translation, 1 = fused one-pass
+        kernel, 2 = fused kernel refuted and redone two-pass; slow_chunks = fused chunks that overflowed their slots."""
+        f, sl = C.c_uint32(0), C.c_uint32(0)
+        _raise(self._lib.hb_ctx_last_decode_path(self._h, C.byref(f), C.byref(sl)))
+        return f.value, sl.value
+
     def stream(self) -> int:
         return int(self._lib.hb_ctx_stream(self._h) or 0)
 

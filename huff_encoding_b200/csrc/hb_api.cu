@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -12,6 +13,7 @@
 #include <string>
 
 #include "hb_decode.cuh"
+#include "hb_decode_fused.cuh"
 #include "hb_encode.cuh"
 #include "hb_fixed.cuh"
 #include "hb_hist.cuh"
@@ -100,7 +102,15 @@ struct hb_ctx {
 
     // decoder
     hb::DecTables *d_dec_tables = nullptr;
-    uint32_t *d_emit = nullptr;          // multi-letter emit table of the fused decoder (1 << kEmitBitsMax entries)
+    uint32_t *d_emit = nullptr;          // multi-letter emit table of the fused decoder (1 << kEmitBits entries)
+    uint8_t *d_code_len = nullptr;       // 256 code lengths (fused decoder: letter-by-letter tails)
+    DevBuf<unsigned long long> fused_desc;
+    uint32_t *d_fused_ctl = nullptr;     // [0] ticket, then a FusedResult (16-byte aligned)
+    hb::FusedResult *h_fused_result = nullptr;   // pinned
+    bool fused_enabled = true;           // HB_NO_FUSED=1: always take the two-pass decoder
+    uint32_t fused_slot_words_forced = 0;        // HB_FUSED_SLOT_WORDS (tests: provoke slot overflow)
+    uint32_t last_fused = 0;             // 1: the last decompress ran the fused kernel, 2: it was refuted and redone two-pass
+    uint32_t last_fused_slow_chunks = 0;
     hb_tree dec_tree_cached;
     bool dec_tree_valid = false;         // dec_tree_cached / dec_fixed_len describe the last tree seen
     bool dec_tables_valid = false;       // d_dec_tables / d_emit were built for dec_tree_cached
@@ -337,8 +347,9 @@ hb_status ensure_dec_tables(hb_ctx *ctx) {
     }
     tp.root = tree.root;
     tp.n_nodes = n;
-    tp.emit_bits = 0;
-    hb::dec_tables_kernel<<<1, hb::kTabThreads, 0, ctx->stream>>>(tp, ctx->d_dec_tables, ctx->d_emit, hb::kCntBits);
+    tp.emit_bits = hb::kEmitBits;
+    for (int b = 0; b < 256; b++) tp.code_len[b] = tree.has_code[b] ? static_cast<uint8_t>(std::min<uint32_t>(tree.code_len[b], 255)) : 0;
+    hb::dec_tables_kernel<<<1, hb::kTabThreads, 0, ctx->stream>>>(tp, ctx->d_dec_tables, ctx->d_emit, ctx->d_code_len, hb::kCntBits);
     ctx->launches++;
     HB_CUDA(cudaGetLastError());
     ctx->dec_tables_valid = true;
@@ -461,6 +472,95 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
     return HB_OK;
 }
 
+// ---------------------------------------------------------------- fused one-pass decoder (hb_decode_fused.cuh)
+// Slot size for a tree: the expected letters of one subsequence (from the leaf weights when the tree carries them,
+// else from the distribution its code lengths imply) with 30 % head-room + the 32 bytes a thread may pull to complete
+// its last output row.  0 = the tree is not eligible / no team would fit.
+uint32_t fused_slot_words(const hb_ctx *ctx, const hb_tree *tree, int *teams_out) {
+    if (!ctx->fused_enabled) return 0;
+    if (tree->max_len > static_cast<uint32_t>(hb::kEmitBits) || tree->n_leaves < 2) return 0;
+    uint32_t coded = 0;
+    for (int b = 0; b < 256; b++) coded += tree->has_code[b] ? 1u : 0u;
+    if (coded != tree->n_leaves) return 0;                     // duplicate letters (ByteWeights quirk): two-pass decoder
+    double num = 0, den = 0;
+    for (uint32_t i = 0; i < tree->n_nodes; i++) {
+        const hb_node &nd = tree->nodes[i];
+        if (nd.left != HB_NO_CHILD) continue;
+        const double len = tree->code_len[nd.letter];
+        const double w = tree->nodes[tree->root].weight ? static_cast<double>(nd.weight) : std::ldexp(1.0, -static_cast<int>(len));
+        num += w * len;
+        den += w;
+    }
+    const double avg = den > 0 ? std::max(1.0, num / den) : 8.0;
+    const double expected = hb::kFSubBits / avg;
+    const size_t budget = 232448 - hb::fused_shared_bytes();
+    auto words_for = [&](double margin) { return (static_cast<uint32_t>(expected * margin + 40.0) / 4 + 1) | 1u; };
+    uint32_t words = ctx->fused_slot_words_forced ? (ctx->fused_slot_words_forced | 1u) : words_for(1.30);
+    int teams = static_cast<int>(budget / hb::fused_team_bytes(words));
+    if (teams < 2 && !ctx->fused_slot_words_forced) {          // prefer two teams with a tighter margin over one team
+        const uint32_t tight = words_for(1.12);
+        uint32_t w2 = static_cast<uint32_t>((budget / 2 - hb::kFWinAlloc * 4 - hb::kFTeam * 8 - 64) / (hb::kFTeam * 4));
+        w2 = (w2 - 1) | 1u;
+        if (w2 >= tight) { words = w2; teams = 2; }
+    }
+    if (teams < 1) return 0;
+    *teams_out = std::min(teams, hb::kFMaxTeams);
+    return words;
+}
+
+// Runs the fused kernel.  *refuted = true: a chunk's speculative entry was wrong (or the kernel cannot serve this call) and
+// the caller must run the two-pass decoder instead; the output buffer then holds garbage.
+hb_status run_fused(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits, uint64_t own_begin, uint64_t own_end,
+                    uint64_t entry_bit, uint64_t stream_bit0, const hb_tree *tree, uint32_t slot_words, int teams,
+                    uint8_t *d_out, size_t out_cap, hb_shard_info *info, bool *refuted) {
+    *refuted = false;
+    HB_TRY(ensure_dec_tables(ctx));
+    const uint64_t chunk_bits = static_cast<uint64_t>(hb::kFChunkWords) * 32;
+    const uint64_t first_chunk = own_begin / chunk_bits;
+    const uint64_t n_chunks = (own_end - 1) / chunk_bits - first_chunk + 1;
+    if (n_chunks > 0x7FFFFFFFull) return HB_ERR_INVALID_ARG;
+    HB_TRY(ctx->fused_desc.reserve(n_chunks));
+    hb::FusedResult *d_result = reinterpret_cast<hb::FusedResult *>(ctx->d_fused_ctl + 4);
+    HB_CUDA(cudaMemsetAsync(ctx->fused_desc.p, 0, n_chunks * sizeof(unsigned long long), ctx->stream));
+    HB_CUDA(cudaMemsetAsync(ctx->d_fused_ctl, 0, 16 + sizeof(hb::FusedResult), ctx->stream));
+
+    hb::FusedParams p;
+    p.words = reinterpret_cast<const uint32_t *>(d_buf);
+    p.n_words_readable = (avail_bits + 31) / 32;
+    p.avail_bits = avail_bits;
+    p.own_begin = own_begin;
+    p.own_end = own_end;
+    p.entry_bit = entry_bit;
+    p.stream_bit0 = stream_bit0;
+    p.len_gcd = tree->len_gcd ? tree->len_gcd : 1;
+    p.fixed_len = (tree->min_len == tree->max_len) ? tree->max_len : 0;
+    p.first_chunk = static_cast<uint32_t>(first_chunk);
+    p.n_chunks = static_cast<uint32_t>(n_chunks);
+    p.slot_words = slot_words;
+    p.spoil_speculation = ctx->spoil_speculation ? 1u : 0u;
+    p.emit = ctx->d_emit;
+    p.code_len = ctx->d_code_len;
+    p.desc = ctx->fused_desc.p;
+    p.ticket = ctx->d_fused_ctl;
+    p.result = d_result;
+    p.out = d_out;
+    p.out_cap = out_cap;
+    const int grid = static_cast<int>(std::min<uint64_t>(ctx->sm_count, (n_chunks + teams - 1) / teams));
+    const size_t smem = hb::fused_shared_bytes() + static_cast<size_t>(teams) * hb::fused_team_bytes(slot_words);
+    hb::dec_fused_kernel<<<grid, teams * hb::kFTeam, smem, ctx->stream>>>(p);
+    ctx->launches++;
+    HB_CUDA(cudaGetLastError());
+    HB_CUDA(cudaMemcpyAsync(ctx->h_fused_result, d_result, sizeof(hb::FusedResult), cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const hb::FusedResult &r = *ctx->h_fused_result;
+    ctx->last_fused_slow_chunks = r.slow_chunks;
+    if (r.error) { *refuted = true; return HB_OK; }
+    info->entry_bit = r.entry0 == hb::kEnd64 ? static_cast<int64_t>(avail_bits) : static_cast<int64_t>(r.entry0);
+    info->exit_bit = r.exit_last == hb::kEnd64 ? avail_bits : r.exit_last;
+    info->n_letters = r.total_letters;
+    return HB_OK;
+}
+
 hb_status run_write_pass(hb_ctx *ctx, uint8_t *d_out, size_t out_cap) {
     if (!ctx->last_dec_valid) return HB_ERR_INVALID_ARG;
     if (ctx->last_dec_total > out_cap) return HB_ERR_CAPACITY;
@@ -490,6 +590,39 @@ hb_status run_write_pass(hb_ctx *ctx, uint8_t *d_out, size_t out_cap) {
     ctx->launches++;
     HB_CUDA(cudaGetLastError());
     return HB_OK;
+}
+
+// decompress of the owned bit range [own_begin, own_end) of a buffer into d_out: the fused one-pass kernel when the
+// tree and the call allow it, else (or when its speculation was refuted) the two-pass kernels.  With HB_ERR_CAPACITY
+// the count-pass state is kept, so hb_decode_write_dev can still write into a larger buffer.
+hb_status decode_range(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits, uint64_t own_begin, uint64_t own_end,
+                       int64_t entry_bit, uint64_t stream_bit0, const hb_tree *tree, uint8_t *d_out, size_t out_cap,
+                       hb_shard_info *info) {
+    HB_TRY(prepare_dec_tree(ctx, tree));
+    ctx->last_fused = 0;
+    if (own_end > avail_bits) own_end = avail_bits;
+    int teams = 0;
+    uint32_t slot_words = 0;
+    const bool fixed_path = ctx->dec_fixed_len && entry_bit >= 0 && (entry_bit % 8) == 0;
+    if (!fixed_path && entry_bit >= 0 && static_cast<uint64_t>(entry_bit) >= own_begin && own_begin < own_end && d_out &&
+        out_cap && (reinterpret_cast<uintptr_t>(d_buf) & 15) == 0)
+        slot_words = fused_slot_words(ctx, tree, &teams);
+    if (slot_words) {
+        bool refuted = false;
+        HB_TRY(run_fused(ctx, d_buf, avail_bits, own_begin, own_end, static_cast<uint64_t>(entry_bit), stream_bit0, tree,
+                         slot_words, teams, d_out, out_cap, info, &refuted));
+        if (!refuted && info->n_letters <= out_cap) {
+            ctx->last_fused = 1;
+            ctx->last_dec_valid = false;
+            return HB_OK;
+        }
+        ctx->last_fused = 2;                                   // fall through: exact two-pass decode (with repair)
+    }
+    info->entry_bit = entry_bit;
+    HB_TRY(run_count_pass(ctx, d_buf, avail_bits, own_begin, own_end, entry_bit, stream_bit0, tree, info));
+    if (info->n_letters > out_cap) return HB_ERR_CAPACITY;
+    if (info->n_letters && !d_out) return HB_ERR_INVALID_ARG;
+    return run_write_pass(ctx, d_out, out_cap);
 }
 
 }  // namespace
@@ -554,7 +687,13 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
         HB_CUDA(cudaMalloc(&ctx->d_enc_table, sizeof(hb::EncTable)));
         HB_CUDA(cudaMalloc(&ctx->d_total_bits, sizeof(unsigned long long)));
         HB_CUDA(cudaMalloc(&ctx->d_dec_tables, sizeof(hb::DecTables)));
-        HB_CUDA(cudaMalloc(&ctx->d_emit, sizeof(uint32_t) << 13));
+        HB_CUDA(cudaMalloc(&ctx->d_emit, sizeof(uint32_t) << hb::kEmitBits));
+        HB_CUDA(cudaMalloc(&ctx->d_code_len, 256));
+        HB_CUDA(cudaMalloc(&ctx->d_fused_ctl, 16 + sizeof(hb::FusedResult)));
+        HB_CUDA(cudaMallocHost(&ctx->h_fused_result, sizeof(hb::FusedResult)));
+        HB_CUDA(cudaFuncSetAttribute(hb::dec_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        { const char *nf = std::getenv("HB_NO_FUSED"); ctx->fused_enabled = !(nf && nf[0] == '1'); }
+        { const char *sw = std::getenv("HB_FUSED_SLOT_WORDS"); ctx->fused_slot_words_forced = sw ? static_cast<uint32_t>(std::atoi(sw)) : 0; }
         HB_CUDA(cudaMalloc(&ctx->d_fix_enc, 256));
         HB_CUDA(cudaMalloc(&ctx->d_fix_dec, 256));
         { const char *nf = std::getenv("HB_NO_FASTPATH"); ctx->fastpath = !(nf && nf[0] == '1'); }
@@ -595,7 +734,9 @@ hb_status hb_ctx_destroy(hb_ctx *ctx) {
     struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_hist); cudaFree(ctx->d_region_hist); cudaFree(ctx->d_enc_table); cudaFree(ctx->d_total_bits); cudaFree(ctx->d_dec_tables); cudaFree(ctx->d_emit); cudaFree(ctx->d_fix_enc); cudaFree(ctx->d_fix_dec);
+    cudaFree(ctx->d_hist); cudaFree(ctx->d_region_hist); cudaFree(ctx->d_enc_table); cudaFree(ctx->d_total_bits); cudaFree(ctx->d_dec_tables); cudaFree(ctx->d_emit); cudaFree(ctx->d_code_len); cudaFree(ctx->d_fused_ctl); cudaFree(ctx->d_fix_enc);
+    if (ctx->h_fused_result) cudaFreeHost(ctx->h_fused_result);
+    ctx->fused_desc.release(); cudaFree(ctx->d_fix_dec);
     cudaFree(ctx->d_dec_result); cudaFree(ctx->d_n_dirty);
     if (ctx->h_dec_result) cudaFreeHost(ctx->h_dec_result);
     if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
@@ -707,11 +848,24 @@ hb_status hb_decompress_u8_dev(hb_ctx *ctx, const uint8_t *d_comp, size_t comp_l
     info.entry_bit = 0;
     info.exit_bit = 0;
     info.n_letters = 0;
-    HB_TRY(run_count_pass(ctx, d_comp, total_bits, 0, total_bits, 0, 0, tree, &info));
+    const hb_status st = decode_range(ctx, d_comp, total_bits, 0, total_bits, 0, 0, tree, d_out, out_cap, &info);
     *out_n = static_cast<size_t>(info.n_letters);
-    if (info.n_letters > out_cap) return HB_ERR_CAPACITY;
-    if (info.n_letters && !d_out) return HB_ERR_INVALID_ARG;
-    return run_write_pass(ctx, d_out, out_cap);
+    return st;
+}
+
+hb_status hb_decode_shard_dev(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits, uint64_t own_begin,
+                              uint64_t own_end, uint64_t stream_bit0, const hb_tree *tree, hb_shard_info *info,
+                              uint8_t *d_out, size_t out_cap) {
+    HB_ENTER(ctx);
+    if (!d_buf || !tree || !info) return HB_ERR_INVALID_ARG;
+    return decode_range(ctx, d_buf, avail_bits, own_begin, own_end, info->entry_bit, stream_bit0, tree, d_out, out_cap, info);
+}
+
+hb_status hb_ctx_last_decode_path(hb_ctx *ctx, uint32_t *fused, uint32_t *slow_chunks) {
+    if (!ctx) return HB_ERR_INVALID_ARG;
+    if (fused) *fused = ctx->last_fused;
+    if (slow_chunks) *slow_chunks = ctx->last_fused_slow_chunks;
+    return HB_OK;
 }
 
 // ---------------------------------------------------------------- host-buffer API
@@ -851,16 +1005,23 @@ static hb_status decompress_host_common(hb_ctx *ctx, const uint8_t *comp, size_t
     }
     HB_TRY(ctx->stage_in.reserve(comp_len + 16));
     HB_CUDA(cudaMemcpyAsync(ctx->stage_in.p, comp, comp_len, cudaMemcpyHostToDevice, ctx->stream));
+    // the letter count is not known before decoding: size the device staging for the most letters this stream can hold
+    // (every code the tree's shortest), capped by what the caller can take
+    const uint64_t bound = total_bits / std::max<uint32_t>(tree->min_len, 1) + 1;
+    const size_t dev_cap = static_cast<size_t>(dst ? std::min<uint64_t>(bound, cap) : bound);
+    HB_TRY(ctx->stage_out.reserve(dev_cap + 64));
     hb_shard_info info;
-    HB_TRY(run_count_pass(ctx, ctx->stage_in.p, total_bits, 0, total_bits, 0, 0, tree, &info));
+    info.entry_bit = 0;
+    info.exit_bit = 0;
+    info.n_letters = 0;
+    hb_status st = decode_range(ctx, ctx->stage_in.p, total_bits, 0, total_bits, 0, 0, tree, ctx->stage_out.p, dev_cap, &info);
     const size_t n = static_cast<size_t>(info.n_letters);
+    if (st == HB_ERR_CAPACITY) { *out_n = n; return st; }
+    HB_TRY(st);
     if (dst && n > cap) { *out_n = n; return HB_ERR_CAPACITY; }
     uint8_t *host = dst ? dst : static_cast<uint8_t *>(std::malloc(n ? n : 1));
     if (!host) return HB_ERR_NO_MEM;
     if (n) {
-        hb_status rc = ctx->stage_out.reserve(n + 64);
-        if (rc == HB_OK) rc = run_write_pass(ctx, ctx->stage_out.p, n);
-        if (rc != HB_OK) { if (!dst) std::free(host); return rc; }
         cudaError_t e = cudaMemcpyAsync(host, ctx->stage_out.p, n, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { if (!dst) std::free(host); return cuda_fail(e, "D2H of the decoded letters", __LINE__); }

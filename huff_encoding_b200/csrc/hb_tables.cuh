@@ -23,6 +23,7 @@ struct TreeParam {
     uint32_t n_nodes;
     uint32_t emit_bits;                // index width of the emit table to build (0 = do not build it)
     uint32_t pad;
+    uint8_t code_len[256];             // code length per letter (0 = none); copied to the device for the fused decoder
 };
 static_assert(sizeof(TreeParam) <= 4000, "TreeParam must fit the kernel parameter space");
 
@@ -40,7 +41,8 @@ __device__ __forceinline__ uint32_t tab_child(uint32_t nd, uint32_t bit) { retur
 // One CTA.  Fills DecTables (first-level table, multi-letter count table, second-level tables + slot list, node copy)
 // and, when tp.emit_bits != 0, the multi-letter emit table `emit` (1 << emit_bits entries) used by the fused decoder.
 __global__ void __launch_bounds__(kTabThreads)
-dec_tables_kernel(const TreeParam tp, DecTables *__restrict__ t, uint32_t *__restrict__ emit, int cnt_bits) {
+dec_tables_kernel(const TreeParam tp, DecTables *__restrict__ t, uint32_t *__restrict__ emit,
+                  uint8_t *__restrict__ lens_out, int cnt_bits) {
     __shared__ uint32_t s_nodes[HB_MAX_NODES];
     __shared__ uint32_t s_scan[kTabThreads / 32];
     __shared__ uint16_t s_slot_node[256];
@@ -52,6 +54,7 @@ dec_tables_kernel(const TreeParam tp, DecTables *__restrict__ t, uint32_t *__res
         t->nodes[i] = nd;
     }
     if (tid == 0) t->root = tp.root;
+    if (tid < 256 && lens_out) lens_out[tid] = tp.code_len[tid];
     __syncthreads();
     const uint32_t root = tp.root;
     const bool lone = tab_is_leaf(s_nodes[root]);

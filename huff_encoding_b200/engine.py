@@ -124,6 +124,18 @@ class Engine:
                                                 stream_bit0, C.byref(tree.raw), C.byref(info)))
         return info.entry_bit, info.exit_bit, info.n_letters
 
+    def decode_shard(self, buf: torch.Tensor, avail_bits: int, own_begin: int, own_end: int, stream_bit0: int,
+                     tree: HuffTree, entry_bit: int, out: torch.Tensor):
+        """Count + write of a shard with a KNOWN entry in one call (fused one-pass decoder when the tree allows it).
+        Returns (entry_bit, exit_bit, n_letters)."""
+        self._check(buf)
+        self._check(out)
+        info = L.HbShardInfo(entry_bit, 0, 0)
+        with self._ordered():
+            _raise(self.lib.hb_decode_shard_dev(self.ctx.handle, buf.data_ptr(), avail_bits, own_begin, own_end,
+                                                stream_bit0, C.byref(tree.raw), C.byref(info), out.data_ptr(), out.numel()))
+        return info.entry_bit, info.exit_bit, info.n_letters
+
     def decode_write(self, out: torch.Tensor):
         self._check(out)
         with self._ordered():

@@ -84,16 +84,16 @@ class ShardedCodec:
         begin, end = info["start_bit"], info["start_bit"] + info["bits"]
         if marks is not None:
             a = self._event()
-        _, _, n = eng.decode_count(comp_buf, end, begin, end, info["bit_offset"] - begin, info["tree"], entry_bit=begin)
+        if hasattr(eng, "decode_shard"):
+            # one call: the fused one-pass decoder when the tree allows it (the entry of an own shard is known exactly)
+            _, _, n = eng.decode_shard(comp_buf, end, begin, end, info["bit_offset"] - begin, info["tree"], begin, out_buf)
+        else:
+            _, _, n = eng.decode_count(comp_buf, end, begin, end, info["bit_offset"] - begin, info["tree"], entry_bit=begin)
+            if out_buf.numel() < n:
+                raise ValueError("out_buf too small")
+            eng.decode_write(out_buf)
         if marks is not None:
-            marks["dec_count"] = (a, self._event())
-        if out_buf.numel() < n:
-            raise ValueError("out_buf too small")
-        if marks is not None:
-            a = self._event()
-        eng.decode_write(out_buf)
-        if marks is not None:
-            marks["dec_write"] = (a, self._event())
+            marks["decode"] = (a, self._event())
         info["n_letters"] = n
         return n
 

@@ -181,6 +181,17 @@ hb_status hb_decode_count_dev(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_
                               uint64_t own_end, uint64_t stream_bit0, const hb_tree *tree, hb_shard_info *info);
 /* writes the letters counted by the matching hb_decode_count_dev call (same ctx, same arguments) */
 hb_status hb_decode_write_dev(hb_ctx *ctx, uint8_t *d_out, size_t out_cap);
+/* Count + write in one call for a shard whose first code-word start is KNOWN (info->entry_bit >= 0 on entry), e.g. the
+ * shards hb_encode_u8_dev produced (entry = start_bit): takes the one-pass fused decoder (every code word decoded once,
+ * stream read once) when the tree allows it, else the two calls above.  HB_ERR_CAPACITY reports info->n_letters and
+ * leaves the count state for hb_decode_write_dev. */
+hb_status hb_decode_shard_dev(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits, uint64_t own_begin,
+                              uint64_t own_end, uint64_t stream_bit0, const hb_tree *tree, hb_shard_info *info,
+                              uint8_t *d_out, size_t out_cap);
+/* which decoder the last decompress / decode_shard call ran: *fused = 0 two-pass (or fixed-length translation),
+ * 1 fused one-pass, 2 fused refuted and redone two-pass; *slow_chunks = chunks of the fused kernel that overflowed their
+ * shared-memory slots and were written letter by letter.  HB_NO_FUSED=1 at ctx creation disables the fused kernel. */
+hb_status hb_ctx_last_decode_path(hb_ctx *ctx, uint32_t *fused, uint32_t *slow_chunks);
 
 #ifdef __cplusplus
 }

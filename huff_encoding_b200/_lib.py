@@ -98,6 +98,8 @@ SYMBOLS = [
     ("hb_decode_shard_dev", C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _treep,
                                       C.POINTER(HbShardInfo), _vp, C.c_size_t]),
     ("hb_ctx_last_decode_path", C.c_int, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    ("hb_ctx_fused_phase_cycles", C.c_int, [_vp, _u64p]),
+    ("hb_ctx_last_encode_error", C.c_int, [_vp, C.POINTER(C.c_uint32)]),
 ]
 
 _lib = None

@@ -15,6 +15,7 @@
 #include "hb_decode.cuh"
 #include "hb_decode_fused.cuh"
 #include "hb_encode.cuh"
+#include "hb_encode_warps.cuh"
 #include "hb_fixed.cuh"
 #include "hb_hist.cuh"
 #include "hb_tables.cuh"
@@ -82,6 +83,14 @@ struct hb_ctx {
     const uint8_t *region_ptr = nullptr;
     size_t region_n = 0, region_letters = 0;
     bool region_valid = false;
+    // per-sub-region (= per encoder warp) cumulative histograms of the same call (hb_encode_warps.cuh)
+    uint32_t *d_sub_cum = nullptr;       // [sm_count * 32][256]
+    unsigned long long *d_sub_bits = nullptr;   // [sm_count * 32]
+    uint32_t *d_enc_err = nullptr;       // != 0: the last encode met a letter without a usable code
+    uint32_t n_sub = 0, subs_per_cta = 1;
+    size_t sub_letters = 0;
+    uint32_t enc_max_len = 0;
+    bool enc_warps = true;               // HB_NO_ENCODE_WARPS=1: always the region kernel (A/B, tests)
 
     // encoder
     hb::EncTable *d_enc_table = nullptr;
@@ -109,6 +118,7 @@ struct hb_ctx {
     hb::FusedResult *h_fused_result = nullptr;   // pinned
     bool fused_enabled = true;           // HB_NO_FUSED=1: always take the two-pass decoder
     uint32_t fused_slot_words_forced = 0;        // HB_FUSED_SLOT_WORDS (tests: provoke slot overflow)
+    int fused_max_decoders = -1;                 // HB_FUSED_DECODERS: teams of a CTA decoding at once (-1 / 0: all)
     uint32_t last_fused = 0;             // 1: the last decompress ran the fused kernel, 2: it was refuted and redone two-pass
     uint32_t last_fused_slow_chunks = 0;
     hb_tree dec_tree_cached;
@@ -190,19 +200,24 @@ hb_status launch_hist(hb_ctx *ctx, const uint8_t *d_data, size_t n, unsigned lon
     if (n == 0) return HB_OK;
     const size_t region = region_size_for(ctx, n);
     if ((reinterpret_cast<uintptr_t>(d_data) & 15) == 0 && region < (static_cast<size_t>(1) << 32)) {
-        // region variant: global bins + one 256 x u32 histogram per encoder region
-        const int n_regions = static_cast<int>((n + region - 1) / region);
+        // region variant: global bins + one 256 x u32 histogram per encoder region + a running snapshot per sub-region
+        // (a region is 32 sub-regions, one per encoder warp)
         HB_CUDA(cudaMemsetAsync(ctx->d_region_hist, 0, static_cast<size_t>(ctx->sm_count) * 256 * sizeof(uint32_t), ctx->stream));
-        const size_t vecs_per_region = region / 16;
-        int per = static_cast<int>(std::min<size_t>(ctx->hist_ctas_per_sm, (vecs_per_region + hb::kHistThreads - 1) / hb::kHistThreads));
-        if (per < 1) per = 1;
-        hb::hist_regions_kernel<<<n_regions * per, hb::kHistThreads, 0, ctx->stream>>>(d_data, n, region, per, d_hist, ctx->d_region_hist);
+        const size_t sub = region / 32;
+        const uint32_t n_sub = static_cast<uint32_t>((n + sub - 1) / sub);
+        uint32_t spc = 1;
+        while (spc < 32 && (n_sub + spc - 1) / spc > static_cast<uint32_t>(ctx->hist_grid)) spc *= 2;
+        hb::hist_subregions_kernel<<<(n_sub + spc - 1) / spc, hb::kHistThreads, 0, ctx->stream>>>(
+            d_data, n, sub, n_sub, spc, d_hist, ctx->d_region_hist, ctx->d_sub_cum);
         ctx->launches++;
         HB_CUDA(cudaGetLastError());
         ctx->region_ptr = d_data;
         ctx->region_n = n;
         ctx->region_letters = region;
         ctx->region_valid = true;
+        ctx->n_sub = n_sub;
+        ctx->subs_per_cta = spc;
+        ctx->sub_letters = sub;
         return HB_OK;
     }
     // any alignment: per-CTA partials are u32, keep every launch below 2^32 bytes per CTA
@@ -238,6 +253,7 @@ hb_status upload_enc_table(hb_ctx *ctx, const hb_tree *tree) {
     ctx->enc_tree_cached = *tree;
     ctx->enc_tree_valid = true;
     ctx->enc_chunk = max_len <= 16 ? 4 : (max_len <= 32 ? 2 : 1);
+    ctx->enc_max_len = max_len;
     ctx->enc_fixed_len = ctx->fastpath ? tree_fixed_len(tree) : 0;
     if (ctx->enc_fixed_len) {
         uint8_t codes[256];
@@ -256,6 +272,18 @@ hb_status launch_encode_s(hb_ctx *ctx, const uint8_t *d_data, size_t n, uint32_t
         if (!ctx->region_valid) return HB_ERR_INVALID_ARG;
     }
     ctx->region_valid = false;        // consume-once: a different buffer may land on the same address later
+    if (S == 4 && ctx->enc_warps && ctx->enc_max_len <= static_cast<uint32_t>(hb::kEwMaxBits)) {
+        // one sub-region per warp: exact bit offsets from the sub-region histograms, then the barrier-free kernel
+        HB_CUDA(cudaMemsetAsync(ctx->d_enc_err, 0, sizeof(uint32_t), ctx->stream));
+        hb::enc_prepare_kernel<<<(ctx->n_sub * 32 + 255) / 256, 256, 0, ctx->stream>>>(
+            ctx->d_sub_cum, ctx->n_sub, ctx->subs_per_cta, ctx->d_enc_table, ctx->d_sub_bits, ctx->d_enc_err);
+        hb::encode_warps_kernel<<<(ctx->n_sub + hb::kEwWarps - 1) / hb::kEwWarps, hb::kEwThreads, hb::kEwSmemBytes, ctx->stream>>>(
+            d_data, n, ctx->d_enc_table, start_bit, reinterpret_cast<uint32_t *>(d_out), ctx->d_sub_bits, ctx->n_sub,
+            ctx->sub_letters, d_total_bits);
+        ctx->launches += 2;
+        HB_CUDA(cudaGetLastError());
+        return HB_OK;
+    }
     const int n_regions = static_cast<int>((n + ctx->region_letters - 1) / ctx->region_letters);
     hb::encode_regions_kernel<S><<<n_regions, hb::kEncThreads, hb::enc_smem_bytes(S), ctx->stream>>>(
         d_data, n, ctx->d_enc_table, start_bit, reinterpret_cast<uint32_t *>(d_out), ctx->d_region_hist,
@@ -479,6 +507,9 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
 uint32_t fused_slot_words(const hb_ctx *ctx, const hb_tree *tree, int *teams_out) {
     if (!ctx->fused_enabled) return 0;
     if (tree->max_len > static_cast<uint32_t>(hb::kEmitBits) || tree->n_leaves < 2) return 0;
+    // near-fixed-length code sets (all lengths within one bit) resynchronise too slowly for the one speculative entry per
+    // chunk the fused kernel cannot repair: leave them to the two-pass decoder and its repair kernel
+    if (tree->max_len - tree->min_len < 2) return 0;
     uint32_t coded = 0;
     for (int b = 0; b < 256; b++) coded += tree->has_code[b] ? 1u : 0u;
     if (coded != tree->n_leaves) return 0;                     // duplicate letters (ByteWeights quirk): two-pass decoder
@@ -494,17 +525,25 @@ uint32_t fused_slot_words(const hb_ctx *ctx, const hb_tree *tree, int *teams_out
     const double avg = den > 0 ? std::max(1.0, num / den) : 8.0;
     const double expected = hb::kFSubBits / avg;
     const size_t budget = 232448 - hb::fused_shared_bytes();
-    auto words_for = [&](double margin) { return (static_cast<uint32_t>(expected * margin + 40.0) / 4 + 1) | 1u; };
-    uint32_t words = ctx->fused_slot_words_forced ? (ctx->fused_slot_words_forced | 1u) : words_for(1.30);
-    int teams = static_cast<int>(budget / hb::fused_team_bytes(words));
-    if (teams < 2 && !ctx->fused_slot_words_forced) {          // prefer two teams with a tighter margin over one team
-        const uint32_t tight = words_for(1.12);
-        uint32_t w2 = static_cast<uint32_t>((budget / 2 - hb::kFWinAlloc * 4 - hb::kFTeam * 8 - 64) / (hb::kFTeam * 4));
-        w2 = (w2 - 1) | 1u;
-        if (w2 >= tight) { words = w2; teams = 2; }
+    auto words_for = [&](double margin) { return (static_cast<uint32_t>(expected * margin + 44.0) / 4 + 1) | 1u; };
+    auto teams_for = [&](uint32_t w) { return std::min<int>(hb::kFMaxTeams, static_cast<int>(budget / hb::fused_team_bytes(w))); };
+    uint32_t words;
+    if (ctx->fused_slot_words_forced) {
+        words = ctx->fused_slot_words_forced | 1u;
+    } else {
+        // as many teams as a tight margin (12 % above the expected letters) allows, then the roomiest slot that keeps them
+        const uint32_t tight = words_for(1.12), loose = words_for(1.30);
+        const int teams = teams_for(tight);
+        if (teams < 1) return 0;
+        const size_t per_team = budget / teams;
+        uint32_t fit = static_cast<uint32_t>((per_team - hb::kFWinAlloc * 4 - hb::kFTeam * 4 - 128) / (hb::kFTeam * 4));
+        fit = (fit - 1) | 1u;                                   // odd, not larger
+        words = std::max(tight, std::min(loose, fit));
     }
-    if (teams < 1) return 0;
-    *teams_out = std::min(teams, hb::kFMaxTeams);
+    const int teams = teams_for(words);
+    // one team per SM (8 warps) cannot hide the table-lookup latency: measured slower than the two-pass kernels
+    if (teams < (ctx->fused_slot_words_forced ? 1 : 2)) return 0;
+    *teams_out = teams;
     return words;
 }
 
@@ -538,6 +577,9 @@ hb_status run_fused(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits, uint
     p.n_chunks = static_cast<uint32_t>(n_chunks);
     p.slot_words = slot_words;
     p.spoil_speculation = ctx->spoil_speculation ? 1u : 0u;
+    // all teams may decode at once by default: the decode phase is latency-bound and two teams together get through
+    // 1.6x the lookups of one (measured with HB_FUSED_DECODERS=1: 17.9 k cycles alone, 22.5 k for two)
+    p.max_decoders = ctx->fused_max_decoders >= 0 ? static_cast<uint32_t>(ctx->fused_max_decoders) : 0u;
     p.emit = ctx->d_emit;
     p.code_len = ctx->d_code_len;
     p.desc = ctx->fused_desc.p;
@@ -685,6 +727,12 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
         HB_CUDA(cudaMalloc(&ctx->d_hist, 256 * sizeof(unsigned long long)));
         HB_CUDA(cudaMalloc(&ctx->d_region_hist, static_cast<size_t>(ctx->sm_count) * 256 * sizeof(uint32_t)));
         HB_CUDA(cudaMalloc(&ctx->d_enc_table, sizeof(hb::EncTable)));
+        HB_CUDA(cudaMalloc(&ctx->d_sub_cum, static_cast<size_t>(ctx->sm_count) * 32 * 256 * sizeof(uint32_t)));
+        HB_CUDA(cudaMalloc(&ctx->d_sub_bits, static_cast<size_t>(ctx->sm_count) * 32 * sizeof(unsigned long long)));
+        HB_CUDA(cudaMalloc(&ctx->d_enc_err, sizeof(uint32_t)));
+        HB_CUDA(cudaMemset(ctx->d_enc_err, 0, sizeof(uint32_t)));
+        HB_CUDA(cudaFuncSetAttribute(hb::encode_warps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hb::kEwSmemBytes)));
+        { const char *nw = std::getenv("HB_NO_ENCODE_WARPS"); ctx->enc_warps = !(nw && nw[0] == '1'); }
         HB_CUDA(cudaMalloc(&ctx->d_total_bits, sizeof(unsigned long long)));
         HB_CUDA(cudaMalloc(&ctx->d_dec_tables, sizeof(hb::DecTables)));
         HB_CUDA(cudaMalloc(&ctx->d_emit, sizeof(uint32_t) << hb::kEmitBits));
@@ -693,6 +741,7 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
         HB_CUDA(cudaMallocHost(&ctx->h_fused_result, sizeof(hb::FusedResult)));
         HB_CUDA(cudaFuncSetAttribute(hb::dec_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         { const char *nf = std::getenv("HB_NO_FUSED"); ctx->fused_enabled = !(nf && nf[0] == '1'); }
+        { const char *md = std::getenv("HB_FUSED_DECODERS"); ctx->fused_max_decoders = md ? std::atoi(md) : -1; }
         { const char *sw = std::getenv("HB_FUSED_SLOT_WORDS"); ctx->fused_slot_words_forced = sw ? static_cast<uint32_t>(std::atoi(sw)) : 0; }
         HB_CUDA(cudaMalloc(&ctx->d_fix_enc, 256));
         HB_CUDA(cudaMalloc(&ctx->d_fix_dec, 256));
@@ -734,7 +783,7 @@ hb_status hb_ctx_destroy(hb_ctx *ctx) {
     struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_hist); cudaFree(ctx->d_region_hist); cudaFree(ctx->d_enc_table); cudaFree(ctx->d_total_bits); cudaFree(ctx->d_dec_tables); cudaFree(ctx->d_emit); cudaFree(ctx->d_code_len); cudaFree(ctx->d_fused_ctl); cudaFree(ctx->d_fix_enc);
+    cudaFree(ctx->d_hist); cudaFree(ctx->d_region_hist); cudaFree(ctx->d_sub_cum); cudaFree(ctx->d_sub_bits); cudaFree(ctx->d_enc_err); cudaFree(ctx->d_enc_table); cudaFree(ctx->d_total_bits); cudaFree(ctx->d_dec_tables); cudaFree(ctx->d_emit); cudaFree(ctx->d_code_len); cudaFree(ctx->d_fused_ctl); cudaFree(ctx->d_fix_enc);
     if (ctx->h_fused_result) cudaFreeHost(ctx->h_fused_result);
     ctx->fused_desc.release(); cudaFree(ctx->d_fix_dec);
     cudaFree(ctx->d_dec_result); cudaFree(ctx->d_n_dirty);
@@ -859,6 +908,21 @@ hb_status hb_decode_shard_dev(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_
     HB_ENTER(ctx);
     if (!d_buf || !tree || !info) return HB_ERR_INVALID_ARG;
     return decode_range(ctx, d_buf, avail_bits, own_begin, own_end, info->entry_bit, stream_bit0, tree, d_out, out_cap, info);
+}
+
+hb_status hb_ctx_last_encode_error(hb_ctx *ctx, uint32_t *flag) {
+    HB_ENTER(ctx);
+    if (!flag) return HB_ERR_INVALID_ARG;
+    HB_CUDA(cudaMemcpyAsync(ctx->h_total_bits, ctx->d_enc_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *flag = *reinterpret_cast<uint32_t *>(ctx->h_total_bits);
+    return HB_OK;
+}
+
+hb_status hb_ctx_fused_phase_cycles(hb_ctx *ctx, uint64_t out[8]) {
+    if (!ctx || !out) return HB_ERR_INVALID_ARG;
+    for (int k = 0; k < 8; k++) out[k] = ctx->h_fused_result->phase_cycles[k];
+    return HB_OK;
 }
 
 hb_status hb_ctx_last_decode_path(hb_ctx *ctx, uint32_t *fused, uint32_t *slow_chunks) {

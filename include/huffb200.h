@@ -153,10 +153,13 @@ hb_status hb_shard_plan(const uint64_t *hists, size_t n_shards, int order_mode, 
  * call hb_histogram_u8_dev again first (the library cannot see device-side writes).  Writes the stream as if it started at
  * bit `start_bit` (0..31) of d_out[0]: the first start_bit bits are left 0 so a neighbouring shard can be OR-ed in
  * (multi-GPU concatenation).  d_out must hold out_cap >= ceil((start_bit + bits)/8) rounded up to 4 bytes.
- * d_total_bits (device u64, optional) receives the number of code bits written.  Letters without a code emit
- * nothing (callers check with hb_stream_bits first).  No host sync. */
+ * d_total_bits (device u64, optional) receives the number of code bits written.  If the input holds a letter the tree
+ * has no code of 1..64 bits for, the stream is UNDEFINED (callers check with hb_stream_bits first); the warp encoder
+ * records that case and hb_ctx_last_encode_error reports it.  No host sync. */
 hb_status hb_encode_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, const hb_tree *tree, uint32_t start_bit,
                            uint8_t *d_out, size_t out_cap, uint64_t *d_total_bits);
+/* synchronises the ctx stream; *flag != 0: the last hb_encode_u8_dev met a letter without a usable code */
+hb_status hb_ctx_last_encode_error(hb_ctx *ctx, uint32_t *flag);
 /* compress() on device buffers: histogram -> (sync) host tree -> encode.  *comp_len / *padding_bits are exact. */
 hb_status hb_compress_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, int order_mode, hb_tree *tree_out,
                              uint8_t *d_out, size_t out_cap, size_t *comp_len, uint8_t *padding_bits);
@@ -192,6 +195,9 @@ hb_status hb_decode_shard_dev(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_
  * 1 fused one-pass, 2 fused refuted and redone two-pass; *slow_chunks = chunks of the fused kernel that overflowed their
  * shared-memory slots and were written letter by letter.  HB_NO_FUSED=1 at ctx creation disables the fused kernel. */
 hb_status hb_ctx_last_decode_path(hb_ctx *ctx, uint32_t *fused, uint32_t *slow_chunks);
+/* profiling aid: SM clock cycles the teams of the last fused decode spent per phase, summed over chunks
+ * (stage, decode, verify, scan, look-back, compaction), out[6] = number of chunks */
+hb_status hb_ctx_fused_phase_cycles(hb_ctx *ctx, uint64_t out[8]);
 
 #ifdef __cplusplus
 }

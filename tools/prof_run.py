@@ -15,9 +15,10 @@ rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 eng = Engine(0)
 d = (G.zipf(size, device=eng.device, s=(15, 10)) if workload == "zipf15" else getattr(G, workload)(size, device=eng.device))
 torch.cuda.synchronize()
+dst = torch.empty(d.numel() + 64, dtype=torch.uint8, device=eng.device)
 for r in range(rounds):
     out, n, pad, tree = eng.compress(d)
-    dec, m = eng.decompress(out, n, pad, tree)
+    dec, m = eng.decompress(out, n, pad, tree, out=dst)
     torch.cuda.synchronize()
     assert m == size and torch.equal(dec[:m], d)
 print("prof_run ok", workload, size, n)

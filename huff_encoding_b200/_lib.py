@@ -50,6 +50,11 @@ class HbTree(C.Structure):
     ]
 
 
+class HbShardLayout(C.Structure):
+    _fields_ = [("bit_offset", C.c_uint64), ("bits", C.c_uint64), ("total_bits", C.c_uint64), ("comp_len", C.c_size_t),
+                ("start_bit", C.c_uint32), ("padding_bits", C.c_uint8)]
+
+
 class HbShardInfo(C.Structure):
     _fields_ = [("entry_bit", C.c_int64), ("exit_bit", C.c_uint64), ("n_letters", C.c_uint64)]
 
@@ -100,6 +105,11 @@ SYMBOLS = [
     ("hb_ctx_last_decode_path", C.c_int, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     ("hb_ctx_fused_phase_cycles", C.c_int, [_vp, _u64p]),
     ("hb_ctx_last_encode_error", C.c_int, [_vp, C.POINTER(C.c_uint32)]),
+    ("hb_comm_get_unique_id", C.c_int, [_vp]),
+    ("hb_comm_init", C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    ("hb_comm_finalize", C.c_int, [_vp]),
+    ("hb_compress_shard_dev", C.c_int, [_vp, _vp, C.c_size_t, C.c_int, _treep, _vp, C.c_size_t, C.POINTER(HbShardLayout)]),
+    ("hb_decompress_shard_dev", C.c_int, [_vp, _vp, C.POINTER(HbShardLayout), _treep, _vp, C.c_size_t, _szp]),
 ]
 
 _lib = None

@@ -3,6 +3,8 @@
 #include "../../include/huffb200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -66,6 +68,42 @@ struct DecResult {           // device -> host after the count pass
     uint32_t pad;
 };
 
+}  // namespace
+
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi *nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.lib ? &api : nullptr;
+    tried = true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);        // the copy the process already uses, if any
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) { g_last_error = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "?"); return nullptr; }
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(h, "ncclAllGather"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather) {
+        g_last_error = "libnccl.so.2 lacks the expected symbols";
+        return nullptr;
+    }
+    api.lib = h;
+    return &api;
+}
+hb_status nccl_fail(NcclApi *api, ncclResult_t r, const char *what) {
+    g_last_error = std::string(what) + " failed: " + (api && api->GetErrorString ? api->GetErrorString(r) : "NCCL error");
+    return HB_ERR_CUDA;
+}
 }  // namespace
 
 struct hb_ctx {
@@ -136,6 +174,11 @@ struct hb_ctx {
     uint64_t last_dec_total = 0;
     bool last_dec_valid = false;
 
+    // multi-GPU: one rank of a communicator (NCCL, resolved at run time: hb_comm_init)
+    ncclComm_t comm = nullptr;
+    int comm_ranks = 1, comm_rank = 0;
+    unsigned long long *d_gather = nullptr;      // [comm_ranks][256] gathered shard histograms
+    uint64_t *h_gather = nullptr;                // pinned copy
     // staging for the host-buffer API; two copy streams + events to overlap H2D / kernel / D2H by chunks
     DevBuf<uint8_t> stage_in, stage_out;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -783,6 +826,9 @@ hb_status hb_ctx_destroy(hb_ctx *ctx) {
     struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) { NcclApi *api = nccl_api(); if (api) api->CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    if (ctx->d_gather) cudaFree(ctx->d_gather);
+    if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
     cudaFree(ctx->d_hist); cudaFree(ctx->d_region_hist); cudaFree(ctx->d_sub_cum); cudaFree(ctx->d_sub_bits); cudaFree(ctx->d_enc_err); cudaFree(ctx->d_enc_table); cudaFree(ctx->d_total_bits); cudaFree(ctx->d_dec_tables); cudaFree(ctx->d_emit); cudaFree(ctx->d_code_len); cudaFree(ctx->d_fused_ctl); cudaFree(ctx->d_fix_enc);
     if (ctx->h_fused_result) cudaFreeHost(ctx->h_fused_result);
     ctx->fused_desc.release(); cudaFree(ctx->d_fix_dec);
@@ -930,6 +976,112 @@ hb_status hb_ctx_last_decode_path(hb_ctx *ctx, uint32_t *fused, uint32_t *slow_c
     if (fused) *fused = ctx->last_fused;
     if (slow_chunks) *slow_chunks = ctx->last_fused_slow_chunks;
     return HB_OK;
+}
+
+// ---------------------------------------------------------------- multi-GPU inside the library
+// NCCL is resolved at run time (dlopen): libhuffb200.so has no link-time dependency on it, and inside a process that
+// already carries an NCCL (torch) the same copy is used.
+static_assert(HB_COMM_ID_BYTES == sizeof(ncclUniqueId), "HB_COMM_ID_BYTES must match ncclUniqueId");
+
+hb_status hb_comm_get_unique_id(uint8_t id[HB_COMM_ID_BYTES]) {
+    if (!id) return HB_ERR_INVALID_ARG;
+    NcclApi *api = nccl_api();
+    if (!api) return HB_ERR_CUDA;
+    ncclUniqueId u;
+    const ncclResult_t r = api->GetUniqueId(&u);
+    if (r != ncclSuccess) return nccl_fail(api, r, "ncclGetUniqueId");
+    std::memcpy(id, &u, sizeof u);
+    return HB_OK;
+}
+
+hb_status hb_comm_init(hb_ctx *ctx, int n_ranks, int rank, const uint8_t id[HB_COMM_ID_BYTES]) {
+    HB_ENTER(ctx);
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks || (n_ranks > 1 && !id) || ctx->comm) return HB_ERR_INVALID_ARG;
+    ctx->comm_ranks = n_ranks;
+    ctx->comm_rank = rank;
+    HB_CUDA(cudaMalloc(&ctx->d_gather, static_cast<size_t>(n_ranks) * 256 * sizeof(unsigned long long)));
+    HB_CUDA(cudaMallocHost(&ctx->h_gather, static_cast<size_t>(n_ranks) * 256 * sizeof(uint64_t)));
+    if (n_ranks == 1) return HB_OK;
+    NcclApi *api = nccl_api();
+    if (!api) return HB_ERR_CUDA;
+    ncclUniqueId u;
+    std::memcpy(&u, id, sizeof u);
+    const ncclResult_t r = api->CommInitRank(&ctx->comm, n_ranks, u, rank);
+    if (r != ncclSuccess) { ctx->comm = nullptr; return nccl_fail(api, r, "ncclCommInitRank"); }
+    return HB_OK;
+}
+
+hb_status hb_comm_finalize(hb_ctx *ctx) {
+    HB_ENTER(ctx);
+    if (ctx->comm) {
+        cudaStreamSynchronize(ctx->stream);
+        NcclApi *api = nccl_api();
+        if (api) api->CommDestroy(ctx->comm);
+        ctx->comm = nullptr;
+    }
+    if (ctx->d_gather) { cudaFree(ctx->d_gather); ctx->d_gather = nullptr; }
+    if (ctx->h_gather) { cudaFreeHost(ctx->h_gather); ctx->h_gather = nullptr; }
+    ctx->comm_ranks = 1;
+    ctx->comm_rank = 0;
+    return HB_OK;
+}
+
+// compress() of one contiguous shard of a larger input (weights.rs:293-319 is the reference's only data-parallel piece:
+// split, count, reduce -- here the reduce is ONE all-gather of the shard histograms on the ctx stream).  Every rank calls
+// this with its shard; the concatenation of the shard streams (hb_shard_layout says where each goes; neighbours share at
+// most one byte, to be OR-ed) is bit for bit the stream one GPU produces for the concatenated input.
+hb_status hb_compress_shard_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, int order_mode, hb_tree *tree_out,
+                                uint8_t *d_out, size_t out_cap, hb_shard_layout *layout) {
+    HB_ENTER(ctx);
+    if (!tree_out || !d_out || !layout || (n && !d_data) || !ctx->d_gather) return HB_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_data) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 3)) return HB_ERR_INVALID_ARG;
+    const int G = ctx->comm_ranks;
+    unsigned long long *mine = ctx->d_gather + static_cast<size_t>(ctx->comm_rank) * 256;
+    HB_TRY(launch_hist(ctx, d_data, n, mine));                   // my bins straight into my row of the gather buffer
+    if (G > 1) {
+        NcclApi *api = nccl_api();
+        if (!api || !ctx->comm) return HB_ERR_INVALID_ARG;
+        const ncclResult_t r = api->AllGather(mine, ctx->d_gather, 256, ncclUint64, ctx->comm, ctx->stream);
+        if (r != ncclSuccess) return nccl_fail(api, r, "ncclAllGather");
+    }
+    HB_CUDA(cudaMemcpyAsync(ctx->h_gather, ctx->d_gather, static_cast<size_t>(G) * 256 * sizeof(uint64_t),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));                 // the tree needs the whole histogram
+    uint64_t bits[64];
+    if (G > 64) return HB_ERR_INVALID_ARG;
+    HB_TRY(hb_shard_plan(ctx->h_gather, static_cast<size_t>(G), order_mode, tree_out, bits));   // empty input -> HB_ERR_EMPTY_WEIGHTS
+    for (int b = 0; b < 256; b++)
+        if (tree_out->has_code[b] && tree_out->code_len[b] > HB_MAX_ENCODE_BITS) return HB_ERR_CODE_TOO_LONG;
+    uint64_t offset = 0, total = 0;
+    for (int g = 0; g < G; g++) { if (g < ctx->comm_rank) offset += bits[g]; total += bits[g]; }
+    layout->bit_offset = offset;
+    layout->bits = bits[ctx->comm_rank];
+    layout->total_bits = total;
+    layout->start_bit = static_cast<uint32_t>(offset % 8);
+    layout->padding_bits = static_cast<uint8_t>((8 - total % 8) % 8);
+    layout->comp_len = static_cast<size_t>((layout->start_bit + layout->bits + 7) / 8);
+    if (((layout->comp_len + 3) & ~static_cast<size_t>(3)) > out_cap) return HB_ERR_CAPACITY;
+    if (n == 0) return HB_OK;
+    return launch_encode(ctx, d_data, n, tree_out, layout->start_bit, d_out, nullptr, true);
+}
+
+// decompress() of a shard produced by hb_compress_shard_dev: its first code word starts at layout->start_bit, so no
+// exchange is needed; one-pass fused decoder when the tree allows it.
+hb_status hb_decompress_shard_dev(hb_ctx *ctx, const uint8_t *d_comp, const hb_shard_layout *layout, const hb_tree *tree,
+                                  uint8_t *d_out, size_t out_cap, size_t *out_n) {
+    HB_ENTER(ctx);
+    if (!d_comp || !layout || !tree || !out_n) return HB_ERR_INVALID_ARG;
+    *out_n = 0;
+    if (layout->bits == 0) return HB_OK;
+    const uint64_t begin = layout->start_bit, end = begin + layout->bits;
+    hb_shard_info info;
+    info.entry_bit = static_cast<int64_t>(begin);
+    info.exit_bit = 0;
+    info.n_letters = 0;
+    const hb_status st = decode_range(ctx, d_comp, end, begin, end, static_cast<int64_t>(begin), layout->bit_offset - begin,
+                                      tree, d_out, out_cap, &info);
+    *out_n = static_cast<size_t>(info.n_letters);
+    return st;
 }
 
 // ---------------------------------------------------------------- host-buffer API

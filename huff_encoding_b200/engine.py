@@ -26,6 +26,7 @@ class Engine:
         self.lib = L.load()
         self._hist = torch.zeros(256, dtype=torch.int64, device=self.device)
         self._stream = torch.cuda.ExternalStream(self.ctx.stream(), device=self.device)
+        self.comm_world = None
 
     # -- helpers
     @property
@@ -140,6 +141,42 @@ class Engine:
         self._check(out)
         with self._ordered():
             _raise(self.lib.hb_decode_write_dev(self.ctx.handle, out.data_ptr(), out.numel()))
+
+    # -- multi-GPU inside the library (hb_comm_* / hb_*_shard_dev): one rank per Engine
+    def comm_init(self, world: int, rank: int, unique_id: bytes | None = None):
+        """Bind this engine's ctx to rank `rank` of a `world`-rank communicator owned by the library (NCCL).  Rank 0 gets
+        the id from `comm_unique_id()`; handing it to the other ranks is the host application's job."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        _raise(self.lib.hb_comm_init(self.ctx.handle, world, rank, buf))
+        self.comm_world, self.comm_rank = world, rank
+
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        _raise(self.lib.hb_comm_get_unique_id(buf))
+        return bytes(buf)
+
+    def comm_finalize(self):
+        _raise(self.lib.hb_comm_finalize(self.ctx.handle))
+        self.comm_world = None
+
+    def compress_shard(self, data: torch.Tensor, out: torch.Tensor, order: int = L.HB_ORDER_ASC):
+        """Collective compress() of this rank's contiguous shard: returns (HbShardLayout, HuffTree)."""
+        self._check(data)
+        self._check(out)
+        t, lay = L.HbTree(), L.HbShardLayout()
+        with self._ordered():
+            _raise(self.lib.hb_compress_shard_dev(self.ctx.handle, data.data_ptr(), data.numel(), order, C.byref(t),
+                                                  out.data_ptr(), out.numel(), C.byref(lay)))
+        return lay, HuffTree(t)
+
+    def decompress_shard(self, comp: torch.Tensor, layout, tree: HuffTree, out: torch.Tensor) -> int:
+        self._check(comp)
+        self._check(out)
+        n = C.c_size_t(0)
+        with self._ordered():
+            _raise(self.lib.hb_decompress_shard_dev(self.ctx.handle, comp.data_ptr(), C.byref(layout), C.byref(tree.raw),
+                                                    out.data_ptr(), out.numel(), C.byref(n)))
+        return n.value
 
     # -- host tree from a histogram
     def tree_from_histogram(self, hist: torch.Tensor, order: int = L.HB_ORDER_ASC) -> HuffTree:

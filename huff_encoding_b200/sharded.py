@@ -97,7 +97,33 @@ class ShardedCodec:
         info["n_letters"] = n
         return n
 
+    def init_library_comm(self):
+        """Move the exchange INTO the library: the ctx gets an NCCL communicator (id broadcast over torch.distributed once)
+        and compress()/decompress() of a shard become single C calls (hb_compress_shard_dev / hb_decompress_shard_dev)."""
+        eng = self.eng
+        uid = None
+        if self.world > 1:
+            t = torch.zeros(128, dtype=torch.uint8, device=eng.device)
+            if self.rank == 0:
+                t.copy_(torch.frombuffer(bytearray(eng.comm_unique_id()), dtype=torch.uint8))
+            self.dist.broadcast(t, 0)
+            uid = bytes(t.cpu().numpy().tobytes())
+        eng.comm_init(self.world, self.rank, uid)
+
+    def _library_round_trip(self, data, comp_buf, out_buf):
+        lay, tree = self.eng.compress_shard(data, comp_buf)
+        n = self.eng.decompress_shard(comp_buf, lay, tree, out_buf)
+        raw = tree.raw
+        self.last_info = {"fixed_len": raw.max_len if (raw.min_len == raw.max_len and raw.max_len in (1, 2, 4, 8)) else 0,
+                          "tree": tree, "bits": lay.bits, "bit_offset": lay.bit_offset, "start_bit": lay.start_bit,
+                          "comp_len": lay.comp_len, "total_bits": lay.total_bits, "padding_bits": lay.padding_bits,
+                          "n_letters": n, "all_bits": None}
+
     def round_trip(self, data, comp_buf, out_buf, want_events: bool = False):
+        if not want_events and getattr(self.eng, "comm_world", None) == self.world:
+            # the whole shard round trip inside the library, collectives included: no Python between the kernels
+            self._library_round_trip(data, comp_buf, out_buf)
+            return None
         if self.world == 1 and not want_events:
             # single GPU: the whole of compress() / decompress() runs inside the library (histogram -> host tree ->
             # encode, count -> write), no Python between the kernels
@@ -121,6 +147,11 @@ class ShardedCodec:
         mine = comp_buf[: info["comp_len"]]
         if self.world == 1:
             return mine.cpu().numpy().copy(), info["padding_bits"]
+        if info.get("all_bits") is None:                     # shards compressed inside the library: exchange the sizes
+            b = torch.tensor([info["bits"]], dtype=torch.int64, device=comp_buf.device)
+            parts = [torch.zeros_like(b) for _ in range(self.world)]
+            self.dist.all_gather(parts, b)
+            info["all_bits"] = [int(x.item()) for x in parts]
         cap = max((info["all_bits"][g] + 7) // 8 + 2 for g in range(self.world))
         send = torch.zeros(cap, dtype=torch.uint8, device=comp_buf.device)
         send[: info["comp_len"]] = mine

@@ -199,6 +199,35 @@ hb_status hb_ctx_last_decode_path(hb_ctx *ctx, uint32_t *fused, uint32_t *slow_c
  * (stage, decode, verify, scan, look-back, compaction), out[6] = number of chunks */
 hb_status hb_ctx_fused_phase_cycles(hb_ctx *ctx, uint64_t out[8]);
 
+/* ---------------------------------------------------------------- multi-GPU inside the library (one rank per ctx)
+ * The reference's only data-parallel piece is ByteWeights::threaded_from_bytes (weights.rs:293-319): split the input,
+ * count the parts, reduce.  Here every rank (one process or thread per GPU) owns a contiguous shard of the input and a
+ * ctx; the library owns the communicator (NCCL over NVLink, loaded at run time) and does the one exchange a compress
+ * needs -- an all-gather of the G shard histograms (G x 2 KiB) on the ctx stream -- between its own kernels.
+ *   rank 0:  hb_comm_get_unique_id(id), hand `id` to the other ranks (the host application's transport)
+ *   all:     hb_comm_init(ctx, G, rank, id)   ...   hb_compress_shard_dev / hb_decompress_shard_dev   ...   hb_comm_finalize
+ * hb_comm_init(ctx, 1, 0, NULL) is valid (single GPU, no NCCL needed). */
+#define HB_COMM_ID_BYTES 128
+typedef struct hb_shard_layout {
+    uint64_t bit_offset;     /* where this shard's first bit sits in the whole stream */
+    uint64_t bits;           /* code bits of this shard */
+    uint64_t total_bits;     /* code bits of all shards */
+    size_t   comp_len;       /* bytes of d_out in use: ceil((start_bit + bits) / 8) */
+    uint32_t start_bit;      /* bit_offset % 8: the first start_bit bits of d_out[0] are zero (the neighbour's) */
+    uint8_t  padding_bits;   /* of the whole stream (comp.rs:446) */
+} hb_shard_layout;
+hb_status hb_comm_get_unique_id(uint8_t id[HB_COMM_ID_BYTES]);
+hb_status hb_comm_init(hb_ctx *ctx, int n_ranks, int rank, const uint8_t id[HB_COMM_ID_BYTES]);
+hb_status hb_comm_finalize(hb_ctx *ctx);
+/* compress() over all ranks' shards: histogram kernel -> all-gather -> identical host tree on every rank -> encode at
+ * the shard's global bit offset.  Byte (bit_offset / 8) of the whole stream is d_out[0]; concatenating the shard
+ * buffers (OR-ing the byte two neighbours share) gives exactly the single-GPU stream.  Collective: every rank calls it. */
+hb_status hb_compress_shard_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, int order_mode, hb_tree *tree_out,
+                                uint8_t *d_out, size_t out_cap, hb_shard_layout *layout);
+/* decompress() of the shard hb_compress_shard_dev produced (d_comp readable to comp_len rounded up to 16 bytes). */
+hb_status hb_decompress_shard_dev(hb_ctx *ctx, const uint8_t *d_comp, const hb_shard_layout *layout, const hb_tree *tree,
+                                  uint8_t *d_out, size_t out_cap, size_t *out_n);
+
 #ifdef __cplusplus
 }
 #endif

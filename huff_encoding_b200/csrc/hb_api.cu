@@ -232,9 +232,14 @@ __global__ void set_u64_kernel(unsigned long long *p, unsigned long long v) { *p
 
 // ---------------------------------------------------------------- histogram
 size_t region_size_for(const hb_ctx *ctx, size_t n) {
-    const size_t unit = hb::kEncRoundLetters;
-    const size_t per = (n + ctx->sm_count - 1) / ctx->sm_count;
-    return std::max<size_t>(unit, (per + unit - 1) / unit * unit);
+    // a region (one CTA of the region encoder) is 32 sub-regions (one per warp of the warp encoder); sub-regions are whole
+    // tiles of 1024 letters, and -- once they are large -- whole iterations of the histogram kernel (32 KiB), so that a
+    // sub-region never ends in the middle of one
+    const size_t subs = static_cast<size_t>(ctx->sm_count) * 32;
+    size_t sub = ((n + subs - 1) / subs + 1023) / 1024 * 1024;
+    const size_t step = static_cast<size_t>(hb::kHistUnroll) * hb::kHistThreads * 16;
+    if (sub >= 2 * step) sub = (sub + step - 1) / step * step;
+    return std::max<size_t>(1024, sub) * 32;
 }
 
 hb_status launch_hist(hb_ctx *ctx, const uint8_t *d_data, size_t n, unsigned long long *d_hist) {
@@ -243,15 +248,12 @@ hb_status launch_hist(hb_ctx *ctx, const uint8_t *d_data, size_t n, unsigned lon
     if (n == 0) return HB_OK;
     const size_t region = region_size_for(ctx, n);
     if ((reinterpret_cast<uintptr_t>(d_data) & 15) == 0 && region < (static_cast<size_t>(1) << 32)) {
-        // region variant: global bins + one 256 x u32 histogram per encoder region + a running snapshot per sub-region
-        // (a region is 32 sub-regions, one per encoder warp)
-        HB_CUDA(cudaMemsetAsync(ctx->d_region_hist, 0, static_cast<size_t>(ctx->sm_count) * 256 * sizeof(uint32_t), ctx->stream));
+        // sub-region variant: global bins + one 256 x u32 histogram per SUB-REGION (one per encoder warp; a region of the
+        // region encoder is 32 of them).  One CTA per sub-region.
         const size_t sub = region / 32;
         const uint32_t n_sub = static_cast<uint32_t>((n + sub - 1) / sub);
-        uint32_t spc = 1;
-        while (spc < 32 && (n_sub + spc - 1) / spc > static_cast<uint32_t>(ctx->hist_grid)) spc *= 2;
-        hb::hist_subregions_kernel<<<(n_sub + spc - 1) / spc, hb::kHistThreads, 0, ctx->stream>>>(
-            d_data, n, sub, n_sub, spc, d_hist, ctx->d_region_hist, ctx->d_sub_cum);
+        HB_CUDA(cudaMemsetAsync(ctx->d_sub_cum, 0, static_cast<size_t>(n_sub) * 256 * sizeof(uint32_t), ctx->stream));
+        hb::hist_regions_kernel<<<n_sub, hb::kHistThreads, 0, ctx->stream>>>(d_data, n, sub, 1, d_hist, ctx->d_sub_cum);
         ctx->launches++;
         HB_CUDA(cudaGetLastError());
         ctx->region_ptr = d_data;
@@ -259,7 +261,6 @@ hb_status launch_hist(hb_ctx *ctx, const uint8_t *d_data, size_t n, unsigned lon
         ctx->region_letters = region;
         ctx->region_valid = true;
         ctx->n_sub = n_sub;
-        ctx->subs_per_cta = spc;
         ctx->sub_letters = sub;
         return HB_OK;
     }
@@ -319,7 +320,7 @@ hb_status launch_encode_s(hb_ctx *ctx, const uint8_t *d_data, size_t n, uint32_t
         // one sub-region per warp: exact bit offsets from the sub-region histograms, then the barrier-free kernel
         HB_CUDA(cudaMemsetAsync(ctx->d_enc_err, 0, sizeof(uint32_t), ctx->stream));
         hb::enc_prepare_kernel<<<(ctx->n_sub * 32 + 255) / 256, 256, 0, ctx->stream>>>(
-            ctx->d_sub_cum, ctx->n_sub, ctx->subs_per_cta, ctx->d_enc_table, ctx->d_sub_bits, ctx->d_enc_err);
+            ctx->d_sub_cum, ctx->n_sub, ctx->d_enc_table, ctx->d_sub_bits, ctx->d_enc_err);
         hb::encode_warps_kernel<<<(ctx->n_sub + hb::kEwWarps - 1) / hb::kEwWarps, hb::kEwThreads, hb::kEwSmemBytes, ctx->stream>>>(
             d_data, n, ctx->d_enc_table, start_bit, reinterpret_cast<uint32_t *>(d_out), ctx->d_sub_bits, ctx->n_sub,
             ctx->sub_letters, d_total_bits);
@@ -328,6 +329,8 @@ hb_status launch_encode_s(hb_ctx *ctx, const uint8_t *d_data, size_t n, uint32_t
         return HB_OK;
     }
     const int n_regions = static_cast<int>((n + ctx->region_letters - 1) / ctx->region_letters);
+    hb::hist_fold_regions_kernel<<<n_regions, 256, 0, ctx->stream>>>(ctx->d_sub_cum, ctx->n_sub, ctx->d_region_hist);
+    ctx->launches++;
     hb::encode_regions_kernel<S><<<n_regions, hb::kEncThreads, hb::enc_smem_bytes(S), ctx->stream>>>(
         d_data, n, ctx->d_enc_table, start_bit, reinterpret_cast<uint32_t *>(d_out), ctx->d_region_hist,
         ctx->region_letters, d_total_bits);

@@ -31,23 +31,20 @@ constexpr int kEwStageWords = 516;                             // 31 + 1024 * 15
 constexpr size_t kEwTableBytes = 256 * 256;                    // 256 bytes per letter: entry (b, lane) at b << 8 | lane << 2
 constexpr size_t kEwSmemBytes = kEwTableBytes + 256 * sizeof(uint2) + static_cast<size_t>(kEwWarps) * kEwStageWords * 4 + 256;
 
-// Sub-region bit totals from the CUMULATIVE per-sub-region histograms the histogram kernel wrote (sub_cum[s][b] = count
-// of letter b in the sub-regions of the same histogram CTA up to and including s; `first_of_cta[s]` != 0 marks the
-// first sub-region of a histogram CTA, whose predecessor row does not count).  One warp per sub-region.
+// Sub-region bit totals from the per-sub-region histograms the histogram kernel wrote (sub_hist[s][b] = count of letter
+// b in sub-region s).  One warp per sub-region.
 // err: set to 1 when a letter that occurs has no code of 1..64 bits (the stream is then undefined).
 __global__ void __launch_bounds__(256)
-enc_prepare_kernel(const uint32_t *__restrict__ sub_cum, uint32_t n_sub, uint32_t subs_per_cta,
+enc_prepare_kernel(const uint32_t *__restrict__ sub_hist, uint32_t n_sub,
                    const EncTable *__restrict__ table, unsigned long long *__restrict__ sub_bits, uint32_t *__restrict__ err) {
     const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (s >= n_sub) return;
-    const bool has_prev = (s % subs_per_cta) != 0;
     unsigned long long acc = 0;
     uint32_t bad = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const uint32_t bsym = lane + 32 * k;
-        uint32_t c = sub_cum[static_cast<size_t>(s) * 256 + bsym];
-        if (has_prev) c -= sub_cum[static_cast<size_t>(s - 1) * 256 + bsym];
+        const uint32_t c = sub_hist[static_cast<size_t>(s) * 256 + bsym];
         const uint32_t len = table->lo[bsym].y;
         acc += static_cast<unsigned long long>(c) * len;
         bad |= (c != 0 && len == 0) ? 1u : 0u;

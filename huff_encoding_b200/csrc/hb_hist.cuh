@@ -152,71 +152,13 @@ hist_regions_kernel(const uint8_t *__restrict__ data, size_t n, size_t region_by
 }
 
 
-// Sub-region variant used by compress(): like hist_regions_kernel, and besides every SUB-REGION (one per encoder warp,
-// hb_encode_warps.cuh; a region is 32 of them) gets a snapshot of the CTA's running bins when its last byte has been
-// counted: sub_cum[s][b] = count of b in the sub-regions this CTA has handled up to and including s.  The prepare kernel
-// of the encoder differences neighbouring snapshots.  Snapshots are plain stores; no per-sub-region zeroing.
-// A CTA handles `subs_per_cta` consecutive sub-regions (a divisor of 32, so a CTA never straddles two regions).
-// grid = ceil(n_sub / subs_per_cta); data 16-byte aligned; sub_bytes a multiple of 1024.
-__global__ void __launch_bounds__(kHistThreads, 4)
-hist_subregions_kernel(const uint8_t *__restrict__ data, size_t n, size_t sub_bytes, uint32_t n_sub, uint32_t subs_per_cta,
-                       unsigned long long *__restrict__ hist, uint32_t *__restrict__ region_hist,
-                       uint32_t *__restrict__ sub_cum) {
-    __shared__ uint32_t cols[256 * 32];
-    for (int i = threadIdx.x; i < 256 * 32; i += kHistThreads) cols[i] = 0;
-    __syncthreads();
-    const uint32_t lane_base = static_cast<uint32_t>(__cvta_generic_to_shared(cols)) + (lane_id() << 2);
-    const uint32_t first = blockIdx.x * subs_per_cta;
-    uint32_t total = 0;                                      // threads 0..255: running count of bin threadIdx.x
-    for (uint32_t k = 0; k < subs_per_cta && first + k < n_sub; k++) {
-        const uint32_t s = first + k;
-        const size_t begin = static_cast<size_t>(s) * sub_bytes;
-        if (begin < n) {
-            const size_t end = min(n, begin + sub_bytes);
-            const size_t n_vec = (end - begin) / 16;
-            const uint4 *vec = reinterpret_cast<const uint4 *>(data + begin);
-            size_t i = threadIdx.x;
-            for (; i + (kHistUnroll - 1) * kHistThreads < n_vec; i += kHistUnroll * kHistThreads) {
-                uint4 v[kHistUnroll];
-#pragma unroll
-                for (int u = 0; u < kHistUnroll; u++) v[u] = ld_stream_u4(vec + i + u * kHistThreads);
-#pragma unroll
-                for (int u = 0; u < kHistUnroll; u++) {
-                    hist_word(lane_base, v[u].x);
-                    hist_word(lane_base, v[u].y);
-                    hist_word(lane_base, v[u].z);
-                    hist_word(lane_base, v[u].w);
-                }
-            }
-            for (; i < n_vec; i += kHistThreads) {
-                const uint4 v = ld_stream_u4(vec + i);
-                hist_word(lane_base, v.x);
-                hist_word(lane_base, v.y);
-                hist_word(lane_base, v.z);
-                hist_word(lane_base, v.w);
-            }
-            const size_t tail_begin = begin + n_vec * 16;      // < 16 bytes, only at the very end of the input
-            if (tail_begin + threadIdx.x < end) hist_red(lane_base + (static_cast<uint32_t>(data[tail_begin + threadIdx.x]) << 7));
-        }
-        __syncthreads();
-        // snapshot: two threads per bin fold 16 lane columns each (rotated start -> conflict-free)
-        {
-            const uint32_t b = threadIdx.x >> 1, half = threadIdx.x & 1;
-            uint32_t sum = 0;
-#pragma unroll
-            for (int j = 0; j < 16; j++) sum += cols[b * 32 + ((j + 16 * half + b) & 31)];
-            sum += __shfl_xor_sync(0xFFFFFFFFu, sum, 1);
-            if (half == 0) sub_cum[static_cast<size_t>(s) * 256 + b] = sum;
-            if (half == 0) total = sum;                        // bin b's running count lives in thread 2b
-        }
-        __syncthreads();                                       // the next sub-region's increments must not reach a slow folder
-    }
-    if ((threadIdx.x & 1) == 0 && total) {
-        const uint32_t b = threadIdx.x >> 1;
-        const uint32_t region = first / 32;
-        atomicAdd(hist + b, static_cast<unsigned long long>(total));
-        atomicAdd(region_hist + region * 256 + b, total);
-    }
+// region_hist[r][b] = sum of the 32 sub-region histograms of region r (only the region encoder needs it: codes > 15 bits)
+__global__ void __launch_bounds__(256)
+hist_fold_regions_kernel(const uint32_t *__restrict__ sub_hist, uint32_t n_sub, uint32_t *__restrict__ region_hist) {
+    const uint32_t r = blockIdx.x, b = threadIdx.x;
+    uint32_t sum = 0;
+    for (uint32_t s = r * 32; s < min(n_sub, r * 32 + 32); s++) sum += sub_hist[static_cast<size_t>(s) * 256 + b];
+    region_hist[r * 256 + b] = sum;
 }
 
 }  // namespace hb

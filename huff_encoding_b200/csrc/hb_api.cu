@@ -155,8 +155,7 @@ struct hb_ctx {
     uint32_t *d_fused_ctl = nullptr;     // [0] ticket, then a FusedResult (16-byte aligned)
     hb::FusedResult *h_fused_result = nullptr;   // pinned
     bool fused_enabled = true;           // HB_NO_FUSED=1: always take the two-pass decoder
-    uint32_t fused_slot_words_forced = 0;        // HB_FUSED_SLOT_WORDS (tests: provoke slot overflow)
-    int fused_max_decoders = -1;                 // HB_FUSED_DECODERS: teams of a CTA decoding at once (-1 / 0: all)
+    int fused_teams_forced = 0;                  // HB_FUSED_TEAMS: cap on the teams per CTA (A/B measurements)
     uint32_t last_fused = 0;             // 1: the last decompress ran the fused kernel, 2: it was refuted and redone two-pass
     uint32_t last_fused_slow_chunks = 0;
     hb_tree dec_tree_cached;
@@ -546,11 +545,9 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
     return HB_OK;
 }
 
-// ---------------------------------------------------------------- fused one-pass decoder (hb_decode_fused.cuh)
-// Slot size for a tree: the expected letters of one subsequence (from the leaf weights when the tree carries them,
-// else from the distribution its code lengths imply) with 30 % head-room + the 32 bytes a thread may pull to complete
-// its last output row.  0 = the tree is not eligible / no team would fit.
-uint32_t fused_slot_words(const hb_ctx *ctx, const hb_tree *tree, int *teams_out) {
+// ---------------------------------------------------------------- fused one-kernel decoder (hb_decode_fused.cuh)
+// Number of teams per CTA for a tree the fused kernel can serve, 0 if it cannot.
+int fused_teams(const hb_ctx *ctx, const hb_tree *tree) {
     if (!ctx->fused_enabled) return 0;
     if (tree->max_len > static_cast<uint32_t>(hb::kEmitBits) || tree->n_leaves < 2) return 0;
     // near-fixed-length code sets (all lengths within one bit) resynchronise too slowly for the one speculative entry per
@@ -559,44 +556,16 @@ uint32_t fused_slot_words(const hb_ctx *ctx, const hb_tree *tree, int *teams_out
     uint32_t coded = 0;
     for (int b = 0; b < 256; b++) coded += tree->has_code[b] ? 1u : 0u;
     if (coded != tree->n_leaves) return 0;                     // duplicate letters (ByteWeights quirk): two-pass decoder
-    double num = 0, den = 0;
-    for (uint32_t i = 0; i < tree->n_nodes; i++) {
-        const hb_node &nd = tree->nodes[i];
-        if (nd.left != HB_NO_CHILD) continue;
-        const double len = tree->code_len[nd.letter];
-        const double w = tree->nodes[tree->root].weight ? static_cast<double>(nd.weight) : std::ldexp(1.0, -static_cast<int>(len));
-        num += w * len;
-        den += w;
-    }
-    const double avg = den > 0 ? std::max(1.0, num / den) : 8.0;
-    const double expected = hb::kFSubBits / avg;
     const size_t budget = 232448 - hb::fused_shared_bytes();
-    auto words_for = [&](double margin) { return (static_cast<uint32_t>(expected * margin + 44.0) / 4 + 1) | 1u; };
-    auto teams_for = [&](uint32_t w) { return std::min<int>(hb::kFMaxTeams, static_cast<int>(budget / hb::fused_team_bytes(w))); };
-    uint32_t words;
-    if (ctx->fused_slot_words_forced) {
-        words = ctx->fused_slot_words_forced | 1u;
-    } else {
-        // as many teams as a tight margin (12 % above the expected letters) allows, then the roomiest slot that keeps them
-        const uint32_t tight = words_for(1.12), loose = words_for(1.30);
-        const int teams = teams_for(tight);
-        if (teams < 1) return 0;
-        const size_t per_team = budget / teams;
-        uint32_t fit = static_cast<uint32_t>((per_team - hb::kFWinAlloc * 4 - hb::kFTeam * 4 - 128) / (hb::kFTeam * 4));
-        fit = (fit - 1) | 1u;                                   // odd, not larger
-        words = std::max(tight, std::min(loose, fit));
-    }
-    const int teams = teams_for(words);
-    // one team per SM (8 warps) cannot hide the table-lookup latency: measured slower than the two-pass kernels
-    if (teams < (ctx->fused_slot_words_forced ? 1 : 2)) return 0;
-    *teams_out = teams;
-    return words;
+    int teams = std::min<int>(hb::kFMaxTeams, static_cast<int>(budget / hb::fused_team_bytes()));
+    if (ctx->fused_teams_forced > 0) teams = std::min(teams, ctx->fused_teams_forced);
+    return teams;
 }
 
 // Runs the fused kernel.  *refuted = true: a chunk's speculative entry was wrong (or the kernel cannot serve this call) and
 // the caller must run the two-pass decoder instead; the output buffer then holds garbage.
 hb_status run_fused(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits, uint64_t own_begin, uint64_t own_end,
-                    uint64_t entry_bit, uint64_t stream_bit0, const hb_tree *tree, uint32_t slot_words, int teams,
+                    uint64_t entry_bit, uint64_t stream_bit0, const hb_tree *tree, int teams,
                     uint8_t *d_out, size_t out_cap, hb_shard_info *info, bool *refuted) {
     *refuted = false;
     HB_TRY(ensure_dec_tables(ctx));
@@ -621,11 +590,7 @@ hb_status run_fused(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits, uint
     p.fixed_len = (tree->min_len == tree->max_len) ? tree->max_len : 0;
     p.first_chunk = static_cast<uint32_t>(first_chunk);
     p.n_chunks = static_cast<uint32_t>(n_chunks);
-    p.slot_words = slot_words;
     p.spoil_speculation = ctx->spoil_speculation ? 1u : 0u;
-    // all teams may decode at once by default: the decode phase is latency-bound and two teams together get through
-    // 1.6x the lookups of one (measured with HB_FUSED_DECODERS=1: 17.9 k cycles alone, 22.5 k for two)
-    p.max_decoders = ctx->fused_max_decoders >= 0 ? static_cast<uint32_t>(ctx->fused_max_decoders) : 0u;
     p.emit = ctx->d_emit;
     p.code_len = ctx->d_code_len;
     p.desc = ctx->fused_desc.p;
@@ -634,14 +599,14 @@ hb_status run_fused(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits, uint
     p.out = d_out;
     p.out_cap = out_cap;
     const int grid = static_cast<int>(std::min<uint64_t>(ctx->sm_count, (n_chunks + teams - 1) / teams));
-    const size_t smem = hb::fused_shared_bytes() + static_cast<size_t>(teams) * hb::fused_team_bytes(slot_words);
+    const size_t smem = hb::fused_shared_bytes() + static_cast<size_t>(teams) * hb::fused_team_bytes();
     hb::dec_fused_kernel<<<grid, teams * hb::kFTeam, smem, ctx->stream>>>(p);
     ctx->launches++;
     HB_CUDA(cudaGetLastError());
     HB_CUDA(cudaMemcpyAsync(ctx->h_fused_result, d_result, sizeof(hb::FusedResult), cudaMemcpyDeviceToHost, ctx->stream));
     HB_CUDA(cudaStreamSynchronize(ctx->stream));
     const hb::FusedResult &r = *ctx->h_fused_result;
-    ctx->last_fused_slow_chunks = r.slow_chunks;
+    ctx->last_fused_slow_chunks = r.careful_threads;
     if (r.error) { *refuted = true; return HB_OK; }
     info->entry_bit = r.entry0 == hb::kEnd64 ? static_cast<int64_t>(avail_bits) : static_cast<int64_t>(r.entry0);
     info->exit_bit = r.exit_last == hb::kEnd64 ? avail_bits : r.exit_last;
@@ -690,15 +655,14 @@ hb_status decode_range(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits, u
     ctx->last_fused = 0;
     if (own_end > avail_bits) own_end = avail_bits;
     int teams = 0;
-    uint32_t slot_words = 0;
     const bool fixed_path = ctx->dec_fixed_len && entry_bit >= 0 && (entry_bit % 8) == 0;
     if (!fixed_path && entry_bit >= 0 && static_cast<uint64_t>(entry_bit) >= own_begin && own_begin < own_end && d_out &&
         out_cap && (reinterpret_cast<uintptr_t>(d_buf) & 15) == 0)
-        slot_words = fused_slot_words(ctx, tree, &teams);
-    if (slot_words) {
+        teams = fused_teams(ctx, tree);
+    if (teams > 0) {
         bool refuted = false;
         HB_TRY(run_fused(ctx, d_buf, avail_bits, own_begin, own_end, static_cast<uint64_t>(entry_bit), stream_bit0, tree,
-                         slot_words, teams, d_out, out_cap, info, &refuted));
+                         teams, d_out, out_cap, info, &refuted));
         if (!refuted && info->n_letters <= out_cap) {
             ctx->last_fused = 1;
             ctx->last_dec_valid = false;
@@ -787,8 +751,7 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
         HB_CUDA(cudaMallocHost(&ctx->h_fused_result, sizeof(hb::FusedResult)));
         HB_CUDA(cudaFuncSetAttribute(hb::dec_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         { const char *nf = std::getenv("HB_NO_FUSED"); ctx->fused_enabled = !(nf && nf[0] == '1'); }
-        { const char *md = std::getenv("HB_FUSED_DECODERS"); ctx->fused_max_decoders = md ? std::atoi(md) : -1; }
-        { const char *sw = std::getenv("HB_FUSED_SLOT_WORDS"); ctx->fused_slot_words_forced = sw ? static_cast<uint32_t>(std::atoi(sw)) : 0; }
+        { const char *tf = std::getenv("HB_FUSED_TEAMS"); ctx->fused_teams_forced = tf ? std::atoi(tf) : 0; }
         HB_CUDA(cudaMalloc(&ctx->d_fix_enc, 256));
         HB_CUDA(cudaMalloc(&ctx->d_fix_dec, 256));
         { const char *nf = std::getenv("HB_NO_FASTPATH"); ctx->fastpath = !(nf && nf[0] == '1'); }

@@ -192,8 +192,8 @@ hb_status hb_decode_shard_dev(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_
                               uint64_t own_end, uint64_t stream_bit0, const hb_tree *tree, hb_shard_info *info,
                               uint8_t *d_out, size_t out_cap);
 /* which decoder the last decompress / decode_shard call ran: *fused = 0 two-pass (or fixed-length translation),
- * 1 fused one-pass, 2 fused refuted and redone two-pass; *slow_chunks = chunks of the fused kernel that overflowed their
- * shared-memory slots and were written letter by letter.  HB_NO_FUSED=1 at ctx creation disables the fused kernel. */
+ * 1 fused single kernel, 2 fused refuted and redone two-pass; *slow_chunks = threads of the fused kernel that wrote their
+ * rows letter by letter (end of the stream, ragged head).  HB_NO_FUSED=1 at ctx creation disables the fused kernel. */
 hb_status hb_ctx_last_decode_path(hb_ctx *ctx, uint32_t *fused, uint32_t *slow_chunks);
 /* profiling aid: SM clock cycles the teams of the last fused decode spent per phase, summed over chunks
  * (stage, decode, verify, scan, look-back, compaction), out[6] = number of chunks */

@@ -1,4 +1,4 @@
-"""The fused one-pass decoder (hb_decode_fused.cuh) against the oracle, and its fallbacks.  Bit-exact."""
+"""The fused single-kernel decoder (hb_decode_fused.cuh) against the oracle, and its fallbacks.  Bit-exact."""
 import os
 
 import numpy as np
@@ -33,36 +33,28 @@ def _decode(hb, ctx, data):
     ours = hb.HuffTree.from_weights(hb.build_weights_map(data, ctx=ctx))
     assert ours.read_codes() == tree.codes()
     got = hb.decompress(hb.CompressData(comp, pad, ours), ctx=ctx)
-    assert got.size == data.size and np.array_equal(got, data), (got.size, data.size, int(np.argmax(got[:min(got.size, data.size)] != data[:min(got.size, data.size)])))
+    m = min(got.size, data.size)
+    assert got.size == data.size and np.array_equal(got, data), (got.size, data.size, int(np.argmax(got[:m] != data[:m])))
     return ctx.last_decode_path()
 
 
-@pytest.mark.parametrize("gen,n", [("zipf", 1 << 20), ("zipf", 3_000_017), ("zipf", 4_321_987), ("zipf", (1 << 24) + 5),
-                                   ("zipf", 33 * 1024 * 4 + 1), ("zipf", 1000), ("zipf", 31), ("zipf", 70_000)])
+# around one chunk (256 subsequences of 33 words = 33 792 stream bytes), several chunks, many teams' worth
+SIZES = [31, 1000, 70_000, 1 << 20, 3_000_017, 4_321_987, (1 << 24) + 5]
+
+
+@pytest.mark.parametrize("gen", ["zipf", "english"])
+@pytest.mark.parametrize("n", SIZES)
 def test_fused_path_is_taken_and_exact(hb, gen, n):
     ctx = hb.Context(0)
-    path, slow = _decode(hb, ctx, getattr(G, gen)(n))
+    path, _ = _decode(hb, ctx, getattr(G, gen)(n, seed=n))
     if n >= 70_000:                    # (the tree of a few dozen letters may be near fixed-length: two-pass decoder)
-        assert path == 1 and slow == 0, (path, slow)
-    ctx.close()
-
-
-@pytest.mark.parametrize("n", [1 << 20, 4_321_987, 33 * 1024 * 4 + 1, 31])
-def test_fused_kernel_on_english_with_forced_slots(hb, n):
-    # English-like text packs ~250 letters into a subsequence: only one team's slots fit an SM, so the library picks the
-    # two-pass decoder for it; forcing the slot size runs the fused kernel on it all the same (one team per SM)
-    ctx = _ctx_with(hb, HB_FUSED_SLOT_WORDS="85")
-    path, slow = _decode(hb, ctx, G.english(n))
-    assert path == 1 and slow == 0, (path, slow)
-    ctx.close()
-    ctx = hb.Context(0)
-    assert _decode(hb, ctx, G.english(n))[0] == 0
+        assert path == 1, path
     ctx.close()
 
 
 def test_fused_matches_two_pass(hb):
     a, b = hb.Context(0), _ctx_with(hb, HB_NO_FUSED="1")
-    for gen, n in (("zipf", 2_000_003), ("zipf", 1_234_567)):
+    for gen, n in (("zipf", 2_000_003), ("english", 1_234_567)):
         data = getattr(G, gen)(n, seed=n)
         assert _decode(hb, a, data)[0] == 1
         assert _decode(hb, b, data)[0] == 0
@@ -70,23 +62,21 @@ def test_fused_matches_two_pass(hb):
     b.close()
 
 
-def test_fused_slot_overflow_takes_the_slow_chunk_path(hb):
-    # slots far too small for the letters of a subsequence: every chunk is written letter by letter, still exact
-    ctx = _ctx_with(hb, HB_FUSED_SLOT_WORDS="21")
-    for gen, n in (("zipf", 1_500_001), ("english", 700_003)):
-        path, slow = _decode(hb, ctx, getattr(G, gen)(n))
-        assert path == 1 and slow > 0, (path, slow)
+@pytest.mark.parametrize("teams", ["1", "2", "3"])
+def test_fused_with_fewer_teams_per_cta(hb, teams):
+    ctx = _ctx_with(hb, HB_FUSED_TEAMS=teams)
+    assert _decode(hb, ctx, G.zipf(5_000_011))[0] == 1
     ctx.close()
 
 
-def test_fused_overflow_in_a_dense_region_only(hb):
-    # zipf letters with a long run of the most frequent letter (2-bit code) in the middle: the chunks inside the run hold
-    # ~2.6x the letters the slots were sized for
+def test_fused_dense_and_sparse_regions(hb):
+    # a long run of the most frequent letter (short code: ~2.6x the usual letters per subsequence) and a run of a rare
+    # letter (12-bit code: few letters per subsequence, threads that own no row at all)
     data = G.zipf(6_000_011).copy()
-    data[2_000_000:2_250_000] = 0                            # (short enough not to change the tree much)
+    data[2_000_000:2_250_000] = 0
+    data[4_000_000:4_050_000] = 255
     ctx = hb.Context(0)
-    path, slow = _decode(hb, ctx, data)
-    assert path == 1 and slow > 0, (path, slow)
+    assert _decode(hb, ctx, data)[0] == 1
     ctx.close()
 
 
@@ -100,13 +90,14 @@ def test_fused_refuted_speculation_falls_back(hb):
 def test_fused_skewed_and_near_uniform_trees(hb):
     ctx = hb.Context(0)
     rng = np.random.default_rng(5)
-    # two letters + rare third (min_len 1), and a 200-letter near-uniform alphabet (8-bit-ish codes, not a perfect tree)
+    # two letters + rare third (1-bit code: ~950 letters per subsequence), and a 200-letter near-uniform alphabet
     skew = rng.choice(np.array([65, 66, 67], np.uint8), size=2_000_003, p=[0.9, 0.09, 0.01])
     flat = rng.integers(0, 200, size=1_500_007).astype(np.uint8)
-    # the skewed tree packs ~950 letters into a subsequence: no slot that large fits, the two-pass decoder serves it
     assert _decode(hb, ctx, skew)[0] in (0, 1)
     # codes of 7 and 8 bits only: such sets resynchronise slowly, the library routes them to the two-pass decoder
     assert _decode(hb, ctx, flat)[0] == 0
+    lop = rng.choice(np.arange(5, dtype=np.uint8), size=3_000_001, p=[0.6, 0.2, 0.1, 0.06, 0.04])
+    assert _decode(hb, ctx, lop)[0] == 1
     ctx.close()
 
 
@@ -120,9 +111,14 @@ def test_fused_device_buffers_unaligned_output_and_capacity(hb):
     base = torch.empty(data.size + 256, dtype=torch.uint8, device="cuda")
     for off in (0, 1, 7, 32, 45):
         out = base[off: off + data.size + 64]
+        out.zero_()
         dec, m = eng.decompress(comp, n, pad, tree, out=out)
         assert m == data.size and torch.equal(dec[:m], d), off
         assert eng.ctx.last_decode_path()[0] == 1
+    # an output buffer of exactly n bytes (no slack behind the last row)
+    exact = torch.empty(data.size, dtype=torch.uint8, device="cuda")
+    dec, m = eng.decompress(comp, n, pad, tree, out=exact)
+    assert m == data.size and torch.equal(dec[:m], d)
     # a buffer that is too small: the needed size is reported and a second call with a larger buffer works
     small = torch.empty(1000, dtype=torch.uint8, device="cuda")
     dec, m = eng.decompress(comp, n, pad, tree, out=small)

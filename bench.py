@@ -306,6 +306,19 @@ def e2e_round_trip(api, eng, data, steps, torch, dist, world, np):
             "api": "hb_compress_u8_into + hb_decompress_u8_into (pinned host buffers in and out)"}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this process to the CPUs NVML reports as local to the GPU, so that the pinned host buffers of the e2e
+    measurement are allocated (first touch) on the NUMA node the GPU's PCIe root hangs off.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -318,6 +331,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)          # pinned host buffers are first-touched on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -334,7 +348,18 @@ def run_ours(args):
     eng = Engine(local_rank)
     codec = ShardedCodec(eng, world, rank, dist if world > 1 else None)
     if world > 1:
-        codec.init_library_comm()            # NCCL communicator inside libhuffb200: the timed steps are C calls only
+        # NCCL communicator inside libhuffb200: the timed steps are C calls only.  (NCCL announces its version on the
+        # C-level stdout at the first init; stdout must carry the one JSON line only, so it goes to stderr meanwhile.)
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            codec.init_library_comm()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     n = args.size
     d = dist if world > 1 else None
 
@@ -448,6 +473,7 @@ def run_ours(args):
             "cold_tree_ms_per_step": head["ms_per_step"], "warm_tree_ms_per_step": warm["ms_per_step"],
             "compress_gbs": head["compress_gbs"], "decompress_gbs": head["decompress_gbs"], "decoder": head["decoder"],
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "host_affinity": (f"{len(numa)} CPUs local to the GPU (NVML)" if numa else "not bound"),
         }
         gen = [c for c in configs if c["workload"] == "zipf" and c["bytes_per_gpu"] == (1 << 30)]
         if gen:

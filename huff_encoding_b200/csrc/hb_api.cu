@@ -591,6 +591,8 @@ hb_status run_fused(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits, uint
     p.first_chunk = static_cast<uint32_t>(first_chunk);
     p.n_chunks = static_cast<uint32_t>(n_chunks);
     p.spoil_speculation = ctx->spoil_speculation ? 1u : 0u;
+    p.k1 = 1;
+    p.k4 = 4;
     p.emit = ctx->d_emit;
     p.code_len = ctx->d_code_len;
     p.desc = ctx->fused_desc.p;

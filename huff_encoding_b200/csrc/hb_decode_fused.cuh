@@ -61,10 +61,13 @@ constexpr int kFWinAlloc = kFWinWords + 4;                     // + look-ahead s
 constexpr uint32_t kFWinBits = kFWinWords * 32u;
 constexpr int kEmitBits = HB_EMIT_BITS;
 #ifndef HB_FUSED_LOOKBACK_BITS
-#define HB_FUSED_LOOKBACK_BITS 256       // in-team look-back: a refuted thread costs its whole team (and, through the
+#define HB_FUSED_LOOKBACK_BITS 320       // in-team look-back: a refuted thread costs its whole team (and, through the
 #endif                                   // look-back, every later chunk) a second count, so it is longer than the two-pass one
 constexpr int kFLookbackBits = HB_FUSED_LOOKBACK_BITS;
-constexpr int kFEmitTrips = 5;                                 // two lookups per trip; a row check after every 10 lookups
+#ifndef HB_FUSED_EMIT_TRIPS
+#define HB_FUSED_EMIT_TRIPS 4
+#endif
+constexpr int kFEmitTrips = HB_FUSED_EMIT_TRIPS;               // two lookups per trip; a row check after every 10 lookups
 constexpr int kFRingWords = 16, kFRingStride = 16;             // 64-byte ring per thread, 64-byte aligned; word k of thread t
                                                                // lives at k ^ (t / 2 % 16): lanes on one word hit 32 banks
 // letters a thread may decode beyond the end of its last row before it notices: one block of lookups
@@ -99,6 +102,9 @@ struct FusedParams {
     uint32_t len_gcd, fixed_len;
     uint32_t first_chunk, n_chunks;
     uint32_t spoil_speculation;
+    uint32_t k1, k4;                   // the constants 1 and 4 as PARAMETERS: register moves and small adds written as
+                                       // multiply-adds by them stay on the FMA pipe (the compiler cannot fold them back
+                                       // into ALU-pipe SEL / IADD; the decode loops are ALU-pipe bound: ncu pipe_alu 72 %)
     const uint32_t *emit;              // 1 << kEmitBits entries
     const uint8_t *code_len;           // 256 bytes
     unsigned long long *desc;          // n_chunks, zeroed before the launch
@@ -140,7 +146,10 @@ __device__ __forceinline__ void st_relaxed_ull(unsigned long long *p, unsigned l
 // predicated, never branches.
 struct FReader {
     uint32_t w0, w1, w2, q, wa;        // wa: shared address of the next word to load
-    __device__ __forceinline__ void init(uint32_t win, uint32_t q0) {
+    uint32_t k1, k4;                   // FusedParams::k1 / k4
+    __device__ __forceinline__ void init(uint32_t win, uint32_t q0, uint32_t one = 1u, uint32_t four = 4u) {
+        k1 = one;
+        k4 = four;
         q = q0;
         wa = win + ((q0 >> 5) << 2);
         w0 = lds32(wa);
@@ -157,6 +166,15 @@ struct FReader {
         q = qn;
     }
     __device__ __forceinline__ void step(uint32_t bits) { refill(q + bits); }
+    // hot loops: the predicated register moves and the address bump as multiply-adds (FMA pipe)
+    __device__ __forceinline__ void step_fma(uint32_t bits) {
+        const uint32_t qn = q + bits;
+        const uint32_t r = (qn ^ q) & 32u;
+        asm volatile("{\n\t.reg .pred f;\n\tsetp.ne.u32 f, %4, 0;\n\t@f mad.lo.u32 %0, %1, %5, 0;\n\t@f mad.lo.u32 %1, %2, %5, 0;\n\t"
+                     "@f ld.shared.u32 %2, [%3];\n\t@f mad.lo.u32 %3, %6, %5, %3;\n\t}"
+                     : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(wa) : "r"(r), "r"(k1), "r"(k4) : "memory");
+        q = qn;
+    }
 };
 
 // byte offset of the emit-table entry for the next kEmitBits bits
@@ -169,12 +187,12 @@ __device__ __forceinline__ uint32_t emit_off(uint32_t x) {
 // Advance from q over whole code words: first code-word start >= q_stop, kEnd32 if a code word does not end at or before
 // q_avail.  `letters` counts the code words passed.  (Phase A and the count pass.)
 __device__ __forceinline__ uint32_t fused_run(uint32_t win, uint32_t lut, uint32_t lens, uint32_t q, uint32_t q_stop,
-                                              uint32_t q_avail, uint32_t &letters) {
+                                              uint32_t q_avail, uint32_t &letters, uint32_t k1 = 1u, uint32_t k4 = 4u) {
     letters = 0;
     if (q == kEnd32) return kEnd32;
     if (q >= q_stop) return q;
     FReader rd;
-    rd.init(win, q);
+    rd.init(win, q, k1, k4);
     uint32_t acc = 0;                                      // sum of the entries' top bytes: bits << 4 | count
     const uint32_t q_begin = q;
     const uint32_t lim = min(q_stop, q_avail);
@@ -183,9 +201,9 @@ __device__ __forceinline__ uint32_t fused_run(uint32_t win, uint32_t lut, uint32
 #pragma unroll 1
         while (rd.q <= last2) {
             const uint32_t e1 = lds32(lut + emit_off(rd.peek()));
-            rd.step(e1 >> 28);
+            rd.step_fma(e1 >> 28);
             const uint32_t e2 = lds32(lut + emit_off(rd.peek()));
-            rd.step(e2 >> 28);
+            rd.step_fma(e2 >> 28);
             acc += (e1 >> 24) + (e2 >> 24);
         }
     }
@@ -424,7 +442,7 @@ dec_fused_kernel(const FusedParams p) {
                     if (rem) q0 += p.len_gcd - rem;
                 }
                 uint32_t dummy;
-                entry = fused_run(a_win, a_lut, a_lens, q0, q_lo, q_avail, dummy);
+                entry = fused_run(a_win, a_lut, a_lens, q0, q_lo, q_avail, dummy, p.k1, p.k4);
             }
         }
 
@@ -433,7 +451,7 @@ dec_fused_kernel(const FusedParams p) {
         bool redo = active;
         for (int round = 0;; round++) {
             if (round > kFTeam + 1) asm volatile("trap;");
-            if (redo) exitq = fused_run(a_win, a_lut, a_lens, entry, q_hi, q_avail, count);
+            if (redo) exitq = fused_run(a_win, a_lut, a_lens, entry, q_hi, q_avail, count, p.k1, p.k4);
             s_exit[tt] = exitq;
             if (tt == 0) s_misc[kMFlag] = 0;
             team_sync(team);
@@ -546,7 +564,8 @@ dec_fused_kernel(const FusedParams p) {
                 atomicAdd(&p.result->careful_threads, 1u);
             } else if (target > 32u || p0 == 0) {
                 FReader rd;
-                rd.init(a_win, entry);
+                rd.init(a_win, entry, p.k1, p.k4);
+                const uint32_t k1 = p.k1;
                 uint32_t acc = 0;
                 uint32_t pp = p0;                              // letter position, exact in its low 4 bits
                 uint32_t wp = p0 & ~3u;                        // bytes of completed words (row space)
@@ -561,9 +580,10 @@ dec_fused_kernel(const FusedParams p) {
                     const uint32_t fl = (pn ^ pp) & 4u;        // <= 3 letters per append: at most one word completes
                     uint32_t wa_ring;                          // ring word of row-space byte wp, swizzled: (wp & 60) ^ ring_sw
                     asm("lop3.b32 %0, %1, 60, %2, 0x6a;" : "=r"(wa_ring) : "r"(wp), "r"(ring_sw));
-                    asm volatile("{\n\t.reg .pred f;\n\tsetp.ne.u32 f, %3, 0;\n\t@f st.shared.u32 [%2], %0;\n\t@f mov.u32 %0, %1;\n\t}"
-                                 : "+r"(acc) : "r"(hi), "r"(wa_ring), "r"(fl) : "memory");
-                    wp += fl;
+                    asm volatile("{\n\t.reg .pred f;\n\tsetp.ne.u32 f, %3, 0;\n\t@f st.shared.u32 [%2], %0;\n\t"
+                                 "@f mad.lo.u32 %0, %1, %4, 0;\n\t}"
+                                 : "+r"(acc) : "r"(hi), "r"(wa_ring), "r"(fl), "r"(k1) : "memory");
+                    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(wp) : "r"(fl), "r"(k1));   // wp += fl
                     pp = pn;
                 };
 #pragma unroll 1
@@ -571,10 +591,10 @@ dec_fused_kernel(const FusedParams p) {
 #pragma unroll
                     for (int t2 = 0; t2 < kFEmitTrips; t2++) {
                         const uint32_t e1 = lds32(a_lut + emit_off(rd.peek()));
-                        rd.step(e1 >> 28);
+                        rd.step_fma(e1 >> 28);
                         append(e1);
                         const uint32_t e2 = lds32(a_lut + emit_off(rd.peek()));
-                        rd.step(e2 >> 28);
+                        rd.step_fma(e2 >> 28);
                         append(e2);
                     }
                     if (wp >= flushed + 32u) {                 // a row is complete in the ring: out it goes

@@ -29,6 +29,7 @@ HB_ERR_CUDA = 11
 HB_ERR_INVALID_ARG = 12
 HB_ERR_CODE_TOO_LONG = 13
 HB_ERR_NO_MEM = 14
+HB_ERR_TREE_NODES = 15
 
 HB_ORDER_ASC = 0
 HB_ORDER_BYTEWEIGHTS = 1

@@ -64,6 +64,11 @@ class HuffCudaError(RuntimeError):
     pass
 
 
+class TreeTooLargeError(ValueError):
+    """hb_tree_from_bin met a tree with more than HB_MAX_NODES nodes (HB_ERR_TREE_NODES).  The reference's try_from_bin
+    (tree_inner.rs:522-604) accepts any size; a byte alphabet never produces such a tree, only hand-made input does."""
+
+
 def _raise(status: int, missing: int | None = None):
     if status == L.HB_OK:
         return
@@ -83,6 +88,8 @@ def _raise(status: int, missing: int | None = None):
         raise FromBinError("Provided BitVec is too big for an encoded HuffTree<u8>")
     if status == L.HB_ERR_INVALID_TREE:
         raise CompressedDataFromBytesError("invalid tree in slice")
+    if status == L.HB_ERR_TREE_NODES:
+        raise TreeTooLargeError("foreign tree with more than 513 nodes (more than 257 leaves): beyond hb_tree's capacity")
     if status == L.HB_ERR_BYTES_SHORT:
         raise CompressedDataFromBytesError("slice too short")
     if status == L.HB_ERR_CUDA:

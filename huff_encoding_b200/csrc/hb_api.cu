@@ -701,6 +701,7 @@ const char *hb_status_str(int status) {
         case HB_ERR_INVALID_ARG: return "invalid argument";
         case HB_ERR_CODE_TOO_LONG: return "code longer than 64 bits";
         case HB_ERR_NO_MEM: return "out of host memory";
+        case HB_ERR_TREE_NODES: return "tree has more than 513 nodes (more than 257 leaves)";
         default: return "unknown status";
     }
 }

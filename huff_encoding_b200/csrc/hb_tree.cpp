@@ -248,7 +248,7 @@ hb_status hb_tree_from_bin(const uint8_t *bin, size_t n_bits, hb_tree *tree) {
     while (root < 0) {
         int bit;
         if (!next_bit(bit)) return HB_ERR_BIN_TOO_SMALL;
-        if (tree->n_nodes >= HB_MAX_NODES) return HB_ERR_INVALID_TREE;
+        if (tree->n_nodes >= HB_MAX_NODES) return HB_ERR_TREE_NODES;     // documented cap (huffb200.h)
         uint16_t id = static_cast<uint16_t>(tree->n_nodes++);
         hb_node &nd = tree->nodes[id];
         nd.left = nd.right = HB_NO_CHILD;
@@ -303,7 +303,9 @@ hb_status hb_try_from_bytes(const uint8_t *bytes, size_t n, hb_tree *tree,
     if (n < 5 + tree_len) return HB_ERR_BYTES_SHORT;      // comp.rs:161
     size_t tree_bits = tree_len * 8;
     tree_bits = tree_bits >= tree_pad ? tree_bits - tree_pad : 0;           // comp.rs:164
-    if (hb_tree_from_bin(bytes + 5, tree_bits, tree) != HB_OK) return HB_ERR_INVALID_TREE;
+    const hb_status tst = hb_tree_from_bin(bytes + 5, tree_bits, tree);
+    if (tst == HB_ERR_TREE_NODES) return tst;
+    if (tst != HB_OK) return HB_ERR_INVALID_TREE;
     size_t dlen = n - 5 - tree_len;
     if (dlen == 0) return HB_ERR_EMPTY_COMP;              // comp.rs:179-183 -> :56-58
     if (data_pad > 7) return HB_ERR_BAD_PADDING;          // comp.rs:59-61

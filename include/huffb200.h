@@ -49,7 +49,11 @@ typedef enum hb_status {
     HB_ERR_CUDA           = 11,  /* CUDA runtime failure; hb_last_error() has the text */
     HB_ERR_INVALID_ARG    = 12,
     HB_ERR_CODE_TOO_LONG  = 13,  /* a used letter's code exceeds HB_MAX_ENCODE_BITS */
-    HB_ERR_NO_MEM         = 14
+    HB_ERR_NO_MEM         = 14,
+    HB_ERR_TREE_NODES     = 15   /* hb_tree_from_bin: more than HB_MAX_NODES nodes.  The reference builds a boxed tree of
+                                    any size (tree_inner.rs:522-604); hb_tree is a flat array sized for a byte alphabet
+                                    (256 letters + ByteWeights' duplicate byte-0 leaf).  A foreign tree with more than
+                                    257 leaves (duplicates of duplicates) is refused with this status, never truncated. */
 } hb_status;
 
 /* leaf insertion order into the heap (tree/branch_heap.rs:52-58) */

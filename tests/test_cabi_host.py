@@ -260,3 +260,38 @@ def test_container_differential_on_random_blobs():
         else:
             agree_err += 1
     assert agree_ok > 20 and agree_err > 20
+
+
+def _tree_bits(spec):
+    """preorder bit string of a nested (left, right) / int-letter structure (tree_inner.rs:637-663)"""
+    if isinstance(spec, int):
+        return "0" + format(spec, "08b")
+    return "1" + _tree_bits(spec[0]) + _tree_bits(spec[1])
+
+
+def _pack(bits):
+    n = len(bits)
+    bits = bits + "0" * ((8 - n % 8) % 8)
+    return bytes(int(bits[i:i + 8], 2) for i in range(0, len(bits), 8)), n
+
+
+def test_foreign_tree_with_duplicates_up_to_the_node_cap_and_beyond():
+    """N3: try_from_bin accepts any preorder tree (tree_inner.rs:522-604).  hb_tree holds 513 nodes = 257 leaves: a
+    right-leaning chain with 257 leaves (letters repeat) parses and matches the oracle; 258 leaves is refused with the
+    dedicated status, not truncated and not mistaken for a malformed tree."""
+    from huff_encoding_b200.api import TreeTooLargeError
+
+    def chain(n_leaves):
+        spec = (n_leaves - 1) % 7
+        for k in range(n_leaves - 2, -1, -1):
+            spec = (k % 7, spec)
+        return spec
+
+    raw, n = _pack(_tree_bits(chain(257)))
+    ours = HuffTree.try_from_bin(raw, n)
+    ref = O.tree_from_bin(np.frombuffer(raw, np.uint8), n)
+    assert ours.read_codes() == ref.codes()
+    assert len(ours.read_codes()) == 7                      # duplicates: the last DFS visit wins (tree_inner.rs:396)
+    raw, n = _pack(_tree_bits(chain(258)))
+    with pytest.raises(TreeTooLargeError):
+        HuffTree.try_from_bin(raw, n)

@@ -123,3 +123,24 @@ def test_fused_device_buffers_unaligned_output_and_capacity(hb):
     small = torch.empty(1000, dtype=torch.uint8, device="cuda")
     dec, m = eng.decompress(comp, n, pad, tree, out=small)
     assert m == data.size and torch.equal(dec[:m], d)
+
+
+def test_serial_repair_of_every_chunk_stays_bounded(hb):
+    # worst case of the two-pass decoder: EVERY chunk's speculative entry is wrong (debug switch), so dec_fix_kernel walks all
+    # of them one after the other.  It must stay exact and its cost must stay linear and small per chunk (a chunk is 32 KiB
+    # of stream): ~1000 chunks here, a generous 20 ms per chunk as the bound.
+    import time
+    ctx = _ctx_with(hb, HB_DEBUG_SPOIL_SPECULATION="1")
+    data = G.zipf(48 << 20)
+    comp, pad, tree = O.compress(data)
+    ours = hb.HuffTree.from_weights(hb.build_weights_map(data, ctx=ctx))
+    cd = hb.CompressData(comp, pad, ours)
+    hb.decompress(cd, ctx=ctx)                                   # warm-up (buffers, tables)
+    t0 = time.perf_counter()
+    got = hb.decompress(cd, ctx=ctx)
+    dt = time.perf_counter() - t0
+    assert np.array_equal(got, data)
+    n_chunks = comp.size // 32768
+    assert ctx.last_decode_repairs() >= n_chunks - 2
+    assert dt < 0.02 * n_chunks, (dt, n_chunks)
+    ctx.close()

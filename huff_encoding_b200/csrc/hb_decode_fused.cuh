@@ -68,8 +68,8 @@ constexpr int kFLookbackBits = HB_FUSED_LOOKBACK_BITS;
 #define HB_FUSED_EMIT_TRIPS 4
 #endif
 constexpr int kFEmitTrips = HB_FUSED_EMIT_TRIPS;               // two lookups per trip; a row check after every 10 lookups
-constexpr int kFRingWords = 16, kFRingStride = 16;             // 64-byte ring per thread, 64-byte aligned; word k of thread t
-                                                               // lives at k ^ (t / 2 % 16): lanes on one word hit 32 banks
+constexpr int kFRingWords = 16, kFRingStride = 16;             // 64-byte ring per thread, stored WORD-MAJOR: word k of thread t at
+                                                               // [k][t], so a lane always hits bank t % 32 wherever it is in its ring
 // letters a thread may decode beyond the end of its last row before it notices: one block of lookups
 constexpr int kFOverrunLetters = 31 + 6 * kFEmitTrips;
 static_assert(kEmitBits <= 13 && kEmitBits >= 8, "emit table index width");
@@ -200,10 +200,13 @@ __device__ __forceinline__ uint32_t fused_run(uint32_t win, uint32_t lut, uint32
         const uint32_t last2 = lim - 2 * kEmitBits;        // both lookups of a trip start at or before lim - kEmitBits
 #pragma unroll 1
         while (rd.q <= last2) {
-            const uint32_t e1 = lds32(lut + emit_off(rd.peek()));
-            rd.step_fma(e1 >> 28);
-            const uint32_t e2 = lds32(lut + emit_off(rd.peek()));
-            rd.step_fma(e2 >> 28);
+            // two lookups per peek: the 32 peeked bits always hold a second kEmitBits-bit window behind the first
+            // entry's <= kEmitBits bits, so one refill test serves both
+            const uint32_t x = rd.peek();
+            const uint32_t e1 = lds32(lut + emit_off(x));
+            const uint32_t b1 = e1 >> 28;
+            const uint32_t e2 = lds32(lut + emit_off(x << b1));
+            rd.step_fma(b1 + (e2 >> 28));
             acc += (e1 >> 24) + (e2 >> 24);
         }
     }
@@ -331,9 +334,8 @@ dec_fused_kernel(const FusedParams p) {
     const uint32_t a_lut = b;
     const uint32_t a_lens = b + (1u << kEmitBits) * 4u;
     const uint32_t a_win = b + static_cast<uint32_t>(fused_shared_bytes() + team * fused_team_bytes());
-    // ring word w (byte offset 4 w) of this thread is at ring_sw ^ (4 w): base | swizzle in one constant
-    const uint32_t ring_sw = (a_win + kFWinAlloc * 4u + 48u + static_cast<uint32_t>(tt) * (kFRingStride * 4u)) |
-                             ((static_cast<uint32_t>(tt) >> 1 & 15u) << 2);
+    // ring word k of this thread is at ring_t + k * (4 * kFTeam)
+    const uint32_t ring_t = a_win + kFWinAlloc * 4u + 48u + static_cast<uint32_t>(tt) * 4u;
     const uint32_t a_bar = smem_addr(s_misc + kMBar);
     const uintptr_t out_addr = reinterpret_cast<uintptr_t>(p.out);
     if (tt == 0) {
@@ -578,8 +580,7 @@ dec_fused_kernel(const FusedParams p) {
                     const uint32_t hi = __funnelshift_l(L, 0u, s);
                     const uint32_t pn = pp + (e >> 24);        // adds count (bits 0..1) + junk above bit 3
                     const uint32_t fl = (pn ^ pp) & 4u;        // <= 3 letters per append: at most one word completes
-                    uint32_t wa_ring;                          // ring word of row-space byte wp, swizzled: (wp & 60) ^ ring_sw
-                    asm("lop3.b32 %0, %1, 60, %2, 0x6a;" : "=r"(wa_ring) : "r"(wp), "r"(ring_sw));
+                    const uint32_t wa_ring = ring_t + (wp & 60u) * static_cast<uint32_t>(kFTeam);   // word (wp / 4) % 16, word-major
                     asm volatile("{\n\t.reg .pred f;\n\tsetp.ne.u32 f, %3, 0;\n\t@f st.shared.u32 [%2], %0;\n\t"
                                  "@f mad.lo.u32 %0, %1, %4, 0;\n\t}"
                                  : "+r"(acc) : "r"(hi), "r"(wa_ring), "r"(fl), "r"(k1) : "memory");
@@ -590,18 +591,19 @@ dec_fused_kernel(const FusedParams p) {
                 while (flushed < target) {
 #pragma unroll
                     for (int t2 = 0; t2 < kFEmitTrips; t2++) {
-                        const uint32_t e1 = lds32(a_lut + emit_off(rd.peek()));
-                        rd.step_fma(e1 >> 28);
+                        const uint32_t x = rd.peek();
+                        const uint32_t e1 = lds32(a_lut + emit_off(x));
+                        const uint32_t b1 = e1 >> 28;
+                        const uint32_t e2 = lds32(a_lut + emit_off(x << b1));
+                        rd.step_fma(b1 + (e2 >> 28));
                         append(e1);
-                        const uint32_t e2 = lds32(a_lut + emit_off(rd.peek()));
-                        rd.step_fma(e2 >> 28);
                         append(e2);
                     }
                     if (wp >= flushed + 32u) {                 // a row is complete in the ring: out it goes
                         const uint32_t half = flushed & 32u;
                         uint32_t v[8];
 #pragma unroll
-                        for (int k = 0; k < 8; k++) v[k] = lds32(((half + 4u * k) ^ ring_sw));
+                        for (int k = 0; k < 8; k++) v[k] = lds32(ring_t + (half + 4u * k) * static_cast<uint32_t>(kFTeam));
                         stg256(row_ptr, v);
                         row_ptr += 32;
                         flushed += 32;

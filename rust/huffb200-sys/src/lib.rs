@@ -22,6 +22,8 @@ pub const HB_ERR_CUDA: c_int = 11;
 pub const HB_ERR_INVALID_ARG: c_int = 12;
 pub const HB_ERR_CODE_TOO_LONG: c_int = 13;
 pub const HB_ERR_NO_MEM: c_int = 14;
+pub const HB_ERR_TREE_NODES: c_int = 15;
+pub const HB_COMM_ID_BYTES: usize = 128;
 
 pub const HB_ORDER_ASC: c_int = 0;
 pub const HB_ORDER_BYTEWEIGHTS: c_int = 1;
@@ -113,6 +115,33 @@ extern "C" {
     pub fn hb_decode_count_dev(ctx: *mut hb_ctx, d_buf: *const u8, avail_bits: u64, own_begin: u64, own_end: u64,
                                stream_bit0: u64, tree: *const hb_tree, info: *mut hb_shard_info) -> c_int;
     pub fn hb_decode_write_dev(ctx: *mut hb_ctx, d_out: *mut u8, out_cap: usize) -> c_int;
+    pub fn hb_decode_shard_dev(ctx: *mut hb_ctx, d_buf: *const u8, avail_bits: u64, own_begin: u64, own_end: u64,
+                               stream_bit0: u64, tree: *const hb_tree, info: *mut hb_shard_info, d_out: *mut u8,
+                               out_cap: usize) -> c_int;
+    pub fn hb_ctx_last_decode_path(ctx: *mut hb_ctx, fused: *mut u32, slow_chunks: *mut u32) -> c_int;
+    pub fn hb_ctx_last_encode_error(ctx: *mut hb_ctx, flag: *mut u32) -> c_int;
+    pub fn hb_ctx_fused_phase_cycles(ctx: *mut hb_ctx, out: *mut u64) -> c_int;
+
+    // multi-GPU inside the library: one rank per ctx, NCCL communicator owned by the library (loaded at run time)
+    pub fn hb_comm_get_unique_id(id: *mut u8) -> c_int;
+    pub fn hb_comm_init(ctx: *mut hb_ctx, n_ranks: c_int, rank: c_int, id: *const u8) -> c_int;
+    pub fn hb_comm_finalize(ctx: *mut hb_ctx) -> c_int;
+    pub fn hb_compress_shard_dev(ctx: *mut hb_ctx, d_data: *const u8, n: usize, order_mode: c_int, tree_out: *mut hb_tree,
+                                 d_out: *mut u8, out_cap: usize, layout: *mut hb_shard_layout) -> c_int;
+    pub fn hb_decompress_shard_dev(ctx: *mut hb_ctx, d_comp: *const u8, layout: *const hb_shard_layout,
+                                   tree: *const hb_tree, d_out: *mut u8, out_cap: usize, out_n: *mut usize) -> c_int;
+}
+
+/// Where a shard sits in the whole stream (include/huffb200.h: hb_shard_layout)
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct hb_shard_layout {
+    pub bit_offset: u64,
+    pub bits: u64,
+    pub total_bits: u64,
+    pub comp_len: usize,
+    pub start_bit: u32,
+    pub padding_bits: u8,
 }
 
 /// Sharded decode result (include/huffb200.h: hb_shard_info)

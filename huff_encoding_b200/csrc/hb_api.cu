@@ -1166,6 +1166,58 @@ static hb_status decompress_host_fixed_pipelined(hb_ctx *ctx, const uint8_t *com
     return HB_OK;
 }
 
+// General (variable-length) code set, host buffers, long stream: the stream is cut into slabs; the entry of slab k is the
+// exit of slab k - 1 (known when its fused kernel has finished), so the H2D copy of slab k + 1, the decode of slab k and
+// the D2H copy of the letters of slab k - 1 run concurrently (full-duplex PCIe), like the fixed-length pipeline above.
+// *done = false: nothing usable was produced (speculation refuted, or the caller's buffer is too small) -- the caller
+// takes the unpipelined path, which handles both exactly.
+static hb_status decompress_host_slabs(hb_ctx *ctx, const uint8_t *comp, size_t comp_len, uint64_t total_bits,
+                                       const hb_tree *tree, uint8_t *dst, size_t cap, size_t dev_cap, size_t *out_n,
+                                       bool *done) {
+    *done = false;
+    const int teams = fused_teams(ctx, tree);
+    size_t slab = std::max<size_t>((comp_len + hb_ctx::kPipeEvents - 2) / (hb_ctx::kPipeEvents - 1), static_cast<size_t>(32) << 20);
+    slab = (slab + 255) / 256 * 256;
+    const int n_slabs = static_cast<int>((comp_len + slab - 1) / slab);
+    HB_CUDA(cudaStreamSynchronize(ctx->stream));                     // tables of an earlier call are complete
+    for (int k = 0; k < n_slabs; k++) {
+        const size_t off = static_cast<size_t>(k) * slab, len = std::min(slab, comp_len - off);
+        HB_CUDA(cudaMemcpyAsync(ctx->stage_in.p + off, comp + off, len, cudaMemcpyHostToDevice, ctx->s_h2d));
+        HB_CUDA(cudaEventRecord(ctx->ev_in[k], ctx->s_h2d));
+    }
+    uint64_t entry = 0;
+    size_t base = 0;
+    hb_status rc = HB_OK;
+    for (int k = 0; k < n_slabs && rc == HB_OK; k++) {
+        const uint64_t own_begin = static_cast<uint64_t>(k) * slab * 8;
+        const uint64_t own_end = std::min<uint64_t>(static_cast<uint64_t>(k + 1) * slab * 8, total_bits);
+        if (own_begin >= own_end) break;
+        // the last chunk of a slab straddles into the next slab: its bytes must have arrived too
+        HB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[std::min(k + 1, n_slabs - 1)], 0));
+        hb_shard_info info;
+        bool refuted = false;
+        if (entry < own_end) {
+            rc = run_fused(ctx, ctx->stage_in.p, total_bits, std::max<uint64_t>(own_begin, std::min(entry, own_end)), own_end,
+                           entry, 0, tree, teams, ctx->stage_out.p + base, dev_cap - base, &info, &refuted);
+            if (rc != HB_OK) break;
+            if (refuted || base + info.n_letters > cap) { rc = HB_ERR_CAPACITY; break; }     // -> unpipelined path
+            const size_t n_k = static_cast<size_t>(info.n_letters);
+            if (n_k) HB_CUDA(cudaMemcpyAsync(dst + base, ctx->stage_out.p + base, n_k, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            base += n_k;
+            entry = info.exit_bit;
+        }
+    }
+    cudaStreamSynchronize(ctx->s_h2d);
+    cudaStreamSynchronize(ctx->s_d2h);
+    if (rc == HB_ERR_CAPACITY) return HB_OK;                             // *done stays false
+    HB_TRY(rc);
+    *out_n = base;
+    *done = true;
+    ctx->last_fused = 1;
+    ctx->last_dec_valid = false;
+    return HB_OK;
+}
+
 static hb_status decompress_host_common(hb_ctx *ctx, const uint8_t *comp, size_t comp_len, uint8_t padding_bits,
                                         const hb_tree *tree, uint8_t **out, uint8_t *dst, size_t cap, size_t *out_n) {
     if (out) *out = nullptr;
@@ -1189,12 +1241,19 @@ static hb_status decompress_host_common(hb_ctx *ctx, const uint8_t *comp, size_t
         return HB_OK;
     }
     HB_TRY(ctx->stage_in.reserve(comp_len + 16));
-    HB_CUDA(cudaMemcpyAsync(ctx->stage_in.p, comp, comp_len, cudaMemcpyHostToDevice, ctx->stream));
     // the letter count is not known before decoding: size the device staging for the most letters this stream can hold
     // (every code the tree's shortest), capped by what the caller can take
     const uint64_t bound = total_bits / std::max<uint32_t>(tree->min_len, 1) + 1;
     const size_t dev_cap = static_cast<size_t>(dst ? std::min<uint64_t>(bound, cap) : bound);
     HB_TRY(ctx->stage_out.reserve(dev_cap + 64));
+    // long streams a fused-decodable tree: slab pipeline (H2D of slab k+1 | decode of slab k | D2H of slab k-1)
+    if (dst && comp_len >= (static_cast<size_t>(64) << 20) && fused_teams(ctx, tree) > 0) {
+        bool done = false;
+        HB_TRY(decompress_host_slabs(ctx, comp, comp_len, total_bits, tree, dst, cap, dev_cap, out_n, &done));
+        if (done) return HB_OK;
+        // (refuted speculation or a buffer that is too small: the plain path below decides and reports)
+    }
+    HB_CUDA(cudaMemcpyAsync(ctx->stage_in.p, comp, comp_len, cudaMemcpyHostToDevice, ctx->stream));
     hb_shard_info info;
     info.entry_bit = 0;
     info.exit_bit = 0;

@@ -144,3 +144,21 @@ def test_serial_repair_of_every_chunk_stays_bounded(hb):
     assert ctx.last_decode_repairs() >= n_chunks // 2       # (a blind guess happens to be a code boundary now and then)
     assert dt < 0.02 * n_chunks, (dt, n_chunks)
     ctx.close()
+
+
+def test_host_api_slab_pipelined_general_decode(hb):
+    # >= 64 MiB of stream through hb_decompress_u8_into: slabs of the stream are copied, decoded (fused kernel, entry of a
+    # slab = exit of the one before) and copied back concurrently
+    ctx = hb.Context(0)
+    for gen, n in (("zipf", (120 << 20) + 12345), ("english", (130 << 20) + 1)):
+        data = getattr(G, gen)(n)
+        cd = hb.compress(data, ctx=ctx)
+        assert cd.comp_bytes().size >= (64 << 20)
+        out = np.empty(n + 7, dtype=np.uint8)
+        back = hb.decompress(cd, ctx=ctx, out=out)
+        assert back.size == n and np.array_equal(back, data)
+        assert ctx.last_decode_path()[0] == 1
+        small = np.empty(n - 1000, dtype=np.uint8)           # too small: the exact size is reported, nothing is lost
+        with pytest.raises(Exception):
+            hb.decompress(cd, ctx=ctx, out=small)
+    ctx.close()

@@ -31,6 +31,52 @@ METRIC = "compress+decompress throughput of input (round trip)"
 UNIT = "GB/s"
 
 
+# ---------------------------------------------------------------- fault containment
+class ConfigFailed(Exception):
+    """A secondary config failed on at least one rank (every rank raises it together, see all_ranks_ok)."""
+
+
+class Watchdog:
+    """A stalled run must not hold the GPUs: when nothing ticks for `limit_s` seconds (one rank raised and left a
+    collective unmatched, a kernel hangs ...), rank 0 prints the JSON line it has -- the headline is measured first --
+    and every rank leaves with os._exit; the other ranks wait a little longer so that rank 0 prints first."""
+
+    def __init__(self, rank: int, limit_s: float):
+        self.rank, self.limit_s = rank, limit_s + (0.0 if rank == 0 else 15.0)
+        self.last = time.monotonic()
+        self.line = None                   # rank 0: the JSON line as far as it is known
+        self.headline_done = False         # every rank: the headline is measured (rank 0 holds a printable line)
+        self.done = False
+        self._thread = threading.Thread(target=self._watch, daemon=True)
+        self._thread.start()
+
+    def tick(self):
+        self.last = time.monotonic()
+
+    def _watch(self):
+        while not self.done:
+            time.sleep(1.0)
+            if time.monotonic() - self.last > self.limit_s and not self.done:
+                self.abort(f"no progress for {self.limit_s:.0f} s")
+
+    def abort(self, why: str):
+        sys.stderr.write(f"bench.py rank {self.rank}: {why}; leaving\n")
+        sys.stderr.flush()
+        if self.rank == 0 and self.line is not None:
+            self.line["aborted"] = why
+            print(json.dumps(self.line), flush=True)
+        os._exit(0 if self.headline_done else 1)
+
+
+def all_ranks_ok(ok: bool, torch, dist, dev) -> bool:
+    """True when `ok` holds on every rank (one tiny all-reduce; every rank gets the same answer)."""
+    if dist is None:
+        return ok
+    t = torch.tensor([0 if ok else 1], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item()) == 0
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -228,21 +274,40 @@ def _frac(bytes_, ms, peak):
     return round(bytes_ / (ms * 1e-3) / 1e9 / peak, 4) if ms and ms > 0 else None
 
 
-def measure(codec, eng, datas, comp_buf, out_buf, steps, warmup, torch, dist, world, peak):
+def measure(codec, eng, datas, comp_buf, out_buf, steps, warmup, torch, dist, world, peak, tick=lambda: None):
     """Device-resident round trips over the inputs in `datas`, rotated step by step (so every step meets a tree the
-    context did not see in the previous step).  Returns timing + per-phase CUDA-event breakdown + parity check."""
+    context did not see in the previous step).  Returns timing + per-phase CUDA-event breakdown + parity check.
+    An error on one rank is noted, the schedule of collectives is kept, and all ranks raise ConfigFailed together at
+    the next checkpoint: no rank is left waiting in a collective for one that has gone."""
     stream = eng.stream
+    dev = comp_buf.device
+    errors = []
+
+    def trip(i, **kw):
+        try:
+            return codec.round_trip(datas[i % len(datas)], comp_buf, out_buf, **kw)
+        except Exception as e:                                 # noqa: BLE001 -- reported through the checkpoint
+            if not errors:
+                errors.append(f"{type(e).__name__}: {e}")
+            return None
+
+    def checkpoint(what):
+        tick()
+        if not all_ranks_ok(not errors, torch, dist, dev):
+            raise ConfigFailed(f"{what}: " + (errors[0] if errors else "failed on another rank"))
+
     with torch.cuda.stream(stream):
         for i in range(warmup):
-            codec.round_trip(datas[i % len(datas)], comp_buf, out_buf)
+            trip(i)
         stream.synchronize()
+        checkpoint("warm-up")
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
         for i in range(steps):
-            codec.round_trip(datas[i % len(datas)], comp_buf, out_buf)
+            trip(i)
         ev1.record(stream)
         stream.synchronize()
         torch.cuda.synchronize()
@@ -251,11 +316,16 @@ def measure(codec, eng, datas, comp_buf, out_buf, steps, warmup, torch, dist, wo
         total_ms = ev0.elapsed_time(ev1)
         last = datas[(steps - 1) % len(datas)]
         n = last.numel()
-        assert codec.last_info["n_letters"] == n and torch.equal(out_buf[:n], last), "round trip mismatch"
+        if not errors and not (codec.last_info["n_letters"] == n and torch.equal(out_buf[:n], last)):
+            errors.append("round trip mismatch")
+        checkpoint("timed steps")
         # per-phase breakdown: extra steps with CUDA events between the phases (not part of the timing above)
         k = min(max(steps, 2), 6)
-        marks = [codec.round_trip(datas[i % len(datas)], comp_buf, out_buf, want_events=True) for i in range(k)]
+        marks = [trip(i, want_events=True) for i in range(k)]
         stream.synchronize()
+        if not errors and any(m is None for m in marks):
+            errors.append("phase breakdown: no events")
+        checkpoint("phase breakdown")
     phase = {ph: sum(m[ph][0].elapsed_time(m[ph][1]) for m in marks) / len(marks) for ph in PHASES}
     t = torch.tensor([total_ms] + [phase[ph] for ph in PHASES], dtype=torch.float64, device=last.device)
     if world > 1:
@@ -345,6 +415,8 @@ def run_ours(args):
     from huff_encoding_b200.sharded import ShardedCodec
 
     peak, peak_src = measured_peak_gbs()
+    wd = Watchdog(rank, float(os.environ.get("HB_BENCH_STALL_S", "240")))
+    run_ours.watchdog = wd
     eng = Engine(local_rank)
     codec = ShardedCodec(eng, world, rank, dist if world > 1 else None)
     if world > 1:
@@ -380,15 +452,17 @@ def run_ours(args):
     sampler.start()
     time.sleep(0.05)
     # warm caches first (same input every step), then the timed, rotating run
-    warm = measure(codec, eng, datas[:1], comp_buf, out_buf, max(3, args.steps // 2), args.warmup, torch, d, world, peak)
+    warm = measure(codec, eng, datas[:1], comp_buf, out_buf, max(3, args.steps // 2), args.warmup, torch, d, world, peak, wd.tick)
     sampler.clear()
     launches0 = eng.kernel_launches()
-    head = measure(codec, eng, datas, comp_buf, out_buf, args.steps, args.warmup, torch, d, world, peak)
+    head = measure(codec, eng, datas, comp_buf, out_buf, args.steps, args.warmup, torch, d, world, peak, wd.tick)
     clocks = sampler.stop()
     # measure() runs warm-up + timed + up to 6 event-instrumented steps: count the launches of the timed steps only
     per_step = (eng.kernel_launches() - launches0) / (args.warmup + args.steps + min(max(args.steps, 2), 6))
     launches = int(round(per_step * args.steps))
+    wd.tick()
     e2e = e2e_round_trip(api, eng, datas[0], max(1, min(args.steps, 4)), torch, d, world, np)
+    wd.tick()
     cpu = None
     if world == 1 and rank == 0:
         sample = min(n, 128 << 20)
@@ -397,52 +471,11 @@ def run_ours(args):
                "sample": f"first {sample} B of the workload, compress+decompress once ({cpu_dt:.1f} s); C port of the "
                          "reference algorithm, single thread, one bit-serial decode walk", "split": cpu_split}
     del datas
+    torch.cuda.empty_cache()
 
-    # ---- the other BASELINE configs on the same GPUs: the variable-length (real Huffman) kernels
-    configs = []
-    if not args.no_general:
-        def run_config(label, workload, nbytes, scaling, steps=3, with_e2e=False):
-            ds = [make_workload(workload, nbytes, rank * nbytes, dev, seed_shift=k) for k in range(1 if workload == "fibonacci" else 2)]
-            cb, ob = buffers(max(x.numel() for x in ds))
-            r = measure(codec, eng, ds, cb, ob, steps, 2, torch, d, world, peak)
-            r.update({"config": label, "workload": workload, "n_gpus": world, "scaling": scaling})
-            if with_e2e:
-                r["e2e"] = e2e_round_trip(api, eng, ds[0], 2, torch, d, world, np)
-            configs.append(r)
-            del ds, cb, ob
-            torch.cuda.empty_cache()
-
-        run_config("1 GiB Zipf(1.2) per GPU (north_star: 1-GPU encode and decode on 1 GiB inputs)", "zipf", 1 << 30, "weak",
-                   steps=5, with_e2e=True)
-        if world == 1:
-            run_config("configs[2]: 4 GiB Zipf(1.2) on one GPU", "zipf", 4 << 30, "weak")
-            run_config("configs[4]: Fibonacci-256, 1 836 311 750 B, 40-bit codes", "fibonacci", 0, "weak", steps=2)
-            run_config("Zipf(1.5), 1 GiB: 1.5 % of the letters have codes beyond the 12-bit tables", "zipf15", 1 << 30, "weak")
-        else:
-            run_config(f"configs[2] weak: 4 GiB Zipf(1.2) per GPU x{world}", "zipf", 4 << 30, "weak")
-            run_config(f"configs[2] strong: 4 GiB Zipf(1.2) in total over {world} GPUs", "zipf", (4 << 30) // world, "strong")
-        run_config(f"configs[3]: English-like text, 2 GiB contiguous shard per GPU x{world}", "english", 2 << 30, "weak")
-
-    if world > 1:
-        # bit-exactness of the sharded path (outside every timed region): the gathered shard streams must equal the
-        # stream ONE GPU produces for the concatenated input
-        m = 32 << 20
-        part = make_workload("english", m, rank * m, dev)
-        cb, ob = buffers(m)
-        codec.round_trip(part, cb, ob)                      # the library path (hb_compress_shard_dev over NCCL)
-        assert torch.equal(ob[:m], part)
-        got = codec.gather_stream(cb, codec.last_info)
-        parts = [torch.empty_like(part) for _ in range(world)] if rank == 0 else None
-        dist.gather(part, parts, dst=0)
-        if rank == 0:
-            whole = torch.cat(parts)
-            out1, clen1, pad1, _ = Engine.compress(eng, whole)
-            assert got[1] == pad1 and got[0].size == clen1 and np.array_equal(got[0], out1[:clen1].cpu().numpy()), \
-                "concatenated shard streams differ from the single-GPU stream"
-        sharded_check = "gathered shard streams == single-GPU stream of the concatenated input (32 MiB per rank): ok"
-    else:
-        sharded_check = None
-
+    # ---- the JSON line as far as the headline goes (rank 0); the secondary configs are appended as they complete, and the
+    #      watchdog prints what there is if a later stage stalls
+    line = None
     if rank == 0:
         phase = head["phase_ms"]
         c_bytes = head["comp_bytes_per_gpu"]
@@ -464,26 +497,88 @@ def run_ours(args):
                 "kernels": kern,
                 "compress": {"ms": round(comp_ms, 4), "algorithmic_bytes": 2 * n + c_bytes, "frac": _frac(2 * n + c_bytes, comp_ms, peak)},
                 "decompress": {"ms": phase["decode"], "algorithmic_bytes": n + c_bytes, "frac": _frac(n + c_bytes, phase["decode"], peak)}}
-        cfg = make_config(args, world)
         line = {
             "metric": METRIC, "value": n * world / (head["ms_per_step"] * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": make_config(args, world),
             "comp_bytes_per_gpu": c_bytes,
             "cold_tree_ms_per_step": head["ms_per_step"], "warm_tree_ms_per_step": warm["ms_per_step"],
             "compress_gbs": head["compress_gbs"], "decompress_gbs": head["decompress_gbs"], "decoder": head["decoder"],
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "host_affinity": (f"{len(numa)} CPUs local to the GPU (NVML)" if numa else "not bound"),
         }
-        gen = [c for c in configs if c["workload"] == "zipf" and c["bytes_per_gpu"] == (1 << 30)]
-        if gen:
-            line["general_frac"] = {"encode": gen[0]["frac"]["encode"], "decode": gen[0]["frac"]["decode"],
-                                    "compress": gen[0]["frac"]["compress"], "workload": gen[0]["config"]}
-        if configs:
-            line["configs"] = configs
-        if sharded_check:
-            line["sharded_parity"] = sharded_check
-        print(json.dumps(line))
+        wd.line = line
+    wd.headline_done = True
+    wd.tick()
+
+    if world > 1:
+        # bit-exactness of the sharded path (outside every timed region): the gathered shard streams must equal the
+        # stream ONE GPU produces for the concatenated input
+        m = 32 << 20
+        part = make_workload("english", m, rank * m, dev)
+        cb, ob = buffers(m)
+        torch.cuda.synchronize()
+        codec.round_trip(part, cb, ob)                      # the library path (hb_compress_shard_dev over NCCL)
+        same = bool(torch.equal(ob[:m], part))
+        got = codec.gather_stream(cb, codec.last_info)
+        parts = [torch.empty_like(part) for _ in range(world)] if rank == 0 else None
+        dist.gather(part, parts, dst=0)
+        if rank == 0:
+            whole = torch.cat(parts)
+            out1, clen1, pad1, _ = Engine.compress(eng, whole)
+            same = same and got[1] == pad1 and got[0].size == clen1 and np.array_equal(got[0], out1[:clen1].cpu().numpy())
+            del whole, out1
+            line["sharded_parity"] = ("gathered shard streams == single-GPU stream of the concatenated input "
+                                      "(32 MiB per rank): " + ("ok" if same else "MISMATCH"))
+        del part, cb, ob, parts
+        torch.cuda.empty_cache()
+        wd.tick()
+
+    # ---- the other BASELINE configs on the same GPUs: the variable-length (real Huffman) kernels
+    configs = []
+    if rank == 0:
+        line["configs"] = configs
+    if not args.no_general:
+        def run_config(label, workload, nbytes, scaling, steps=3, with_e2e=False):
+            wd.tick()
+            r = {"config": label, "workload": workload, "n_gpus": world, "scaling": scaling}
+            ds = cb = ob = None
+            try:
+                ds = [make_workload(workload, nbytes, rank * nbytes, dev, seed_shift=k)
+                      for k in range(1 if workload == "fibonacci" else 2)]
+                cb, ob = buffers(max(x.numel() for x in ds))
+                # the inputs are generated on torch's stream; the library's stream does not wait for it by itself
+                torch.cuda.synchronize()
+                r.update(measure(codec, eng, ds, cb, ob, steps, 2, torch, d, world, peak, wd.tick))
+                if with_e2e:
+                    r["e2e"] = e2e_round_trip(api, eng, ds[0], 2, torch, d, world, np)
+            except ConfigFailed as e:                       # raised by every rank together: carry on with the next config
+                r["error"] = str(e)
+                sys.stderr.write(f"bench.py rank {rank}: config '{label}' failed: {e}\n")
+            configs.append(r)
+            if rank == 0 and "general_frac" not in line and "error" not in r and workload == "zipf" and nbytes == (1 << 30):
+                line["general_frac"] = {"encode": r["frac"]["encode"], "decode": r["frac"]["decode"],
+                                        "compress": r["frac"]["compress"], "workload": label}
+            ds = cb = ob = None
+            torch.cuda.empty_cache()
+            wd.tick()
+
+        run_config("1 GiB Zipf(1.2) per GPU (north_star: 1-GPU encode and decode on 1 GiB inputs)", "zipf", 1 << 30, "weak",
+                   steps=5, with_e2e=True)
+        if world == 1:
+            run_config("configs[2]: 4 GiB Zipf(1.2) on one GPU", "zipf", 4 << 30, "weak")
+            run_config("configs[4]: Fibonacci-256, 1 836 311 750 B, 40-bit codes", "fibonacci", 0, "weak", steps=2)
+            run_config("Zipf(1.5), 1 GiB: 1.5 % of the letters have codes of 13 and 14 bits", "zipf15", 1 << 30, "weak")
+        else:
+            run_config(f"configs[2] weak: 4 GiB Zipf(1.2) per GPU x{world}", "zipf", 4 << 30, "weak")
+            run_config(f"configs[2] strong: 4 GiB Zipf(1.2) in total over {world} GPUs", "zipf", (4 << 30) // world, "strong")
+        run_config(f"configs[3]: English-like text, 2 GiB contiguous shard per GPU x{world}", "english", 2 << 30, "weak")
+
+    wd.done = True
+    if rank == 0:
+        if not configs:
+            del line["configs"]
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -501,7 +596,27 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    return run_reference(args) if args.impl == "reference" else run_ours(args)
+    if args.impl == "reference":
+        return run_reference(args)
+    try:
+        return run_ours(args)
+    except BaseException as e:                                  # noqa: BLE001
+        if isinstance(e, SystemExit):
+            raise
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        wd = getattr(run_ours, "watchdog", None)
+        rank = int(os.environ.get("RANK", "0"))
+        if wd is not None and wd.headline_done and rank != 0:
+            # the other ranks are (or will be) waiting for this one in a collective: let rank 0's watchdog print the line
+            # it has, then leave through this rank's own watchdog
+            while True:
+                time.sleep(1.0)
+        if wd is not None:
+            wd.abort(f"{type(e).__name__}: {e}")
+        # a plain `raise` would run the interpreter's teardown, which can wait for ever on a half-finished collective
+        os._exit(1)
 
 
 if __name__ == "__main__":

@@ -19,6 +19,7 @@ ds = [make_workload(workload, size, 0, eng.device, seed_shift=k) for k in range(
 n = max(x.numel() for x in ds)
 comp = torch.empty(n + n // 4 + 4096, dtype=torch.uint8, device=eng.device)
 out = torch.empty(n + 64, dtype=torch.uint8, device=eng.device)
+torch.cuda.synchronize()          # the inputs are generated on torch's stream; the library's stream does not wait for it
 with torch.cuda.stream(eng.stream):
     for i in range(2):
         codec.round_trip(ds[i % len(ds)], comp, out, want_events=True)

@@ -24,6 +24,7 @@ per = n_total // world
 lo, hi = rank * per, (n_total if rank == world - 1 else (rank + 1) * per)
 shard = getattr(G, kind)(hi - lo, offset=lo, device=dev)
 comp_buf = torch.zeros(shard.numel() + shard.numel() // 4 + 4096, dtype=torch.uint8, device=dev)
+torch.cuda.synchronize()        # shard and comp_buf are written on torch's stream; the engine stream must not race it
 with torch.cuda.stream(eng.stream):
     info = codec.compress(shard, comp_buf)
     out_buf = torch.zeros(shard.numel() + 64, dtype=torch.uint8, device=dev)

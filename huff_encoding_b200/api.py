@@ -381,8 +381,8 @@ class CompressData:
         return out[: n.value].tobytes()
 
     @classmethod
-    def try_from_bytes(cls, blob) -> "CompressData":
-        """comp.rs:128-184"""
+    def try_from_bytes(cls, blob, copy: bool = True) -> "CompressData":
+        """comp.rs:128-184.  copy=False keeps comp_bytes a view of `blob` (e.g. a pinned file image)."""
         a = _u8(blob)
         t = L.HbTree()
         off, ln, pad = C.c_size_t(0), C.c_size_t(0), C.c_uint8(0)
@@ -393,7 +393,8 @@ class CompressData:
                    "slice too short to read tree length" if a.size < 5 else "slice too short to read tree")
             raise CompressedDataFromBytesError(msg)
         _raise(st)
-        return cls(a[off.value: off.value + ln.value].copy(), pad.value, HuffTree(t))
+        data = a[off.value: off.value + ln.value]
+        return cls(data.copy() if copy else data, pad.value, HuffTree(t))
 
 
 # ---------------------------------------------------------------- compress / decompress (host buffers)
@@ -420,10 +421,45 @@ def compress(letters, ctx: Context | None = None, out: np.ndarray | None = None)
     return CompressData(_take(ptr, n.value), pad.value, HuffTree(t))
 
 
-def compress_with_tree(letters, huff_tree: HuffTree, ctx: Context | None = None) -> CompressData:
-    """comp.rs:419-451; raises CompressError(missing_letter) when the tree lacks a letter."""
+class PinnedBuffer:
+    """Page-locked host memory from the library (hb_host_alloc): file and network staging that moves over PCIe at full
+    speed and asynchronously.  `.array` is a numpy u8 view; release with close() or use as a context manager."""
+
+    def __init__(self, nbytes: int):
+        self._p = C.c_void_p()
+        _raise(L.load().hb_host_alloc(max(int(nbytes), 1), C.byref(self._p)))
+        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_uint8)), shape=(max(int(nbytes), 1),))[: int(nbytes)]
+
+    def close(self):
+        if self._p:
+            self.array = None
+            L.load().hb_host_free(self._p)
+            self._p = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def compress_with_tree(letters, huff_tree: HuffTree, ctx: Context | None = None, out: np.ndarray | None = None) -> CompressData:
+    """comp.rs:419-451; raises CompressError(missing_letter) when the tree lacks a letter.  `out`: optional
+    caller-owned u8 buffer (e.g. a PinnedBuffer) that receives comp_bytes."""
     a = _u8(letters)
     ctx = ctx or default_context()
+    if out is not None:
+        n, pad, missing = C.c_size_t(0), C.c_uint8(0), C.c_uint8(0)
+        st = L.load().hb_compress_with_tree_u8_into(ctx.handle, a.ctypes.data, a.size, C.byref(huff_tree.raw),
+                                                    out.ctypes.data, out.size, C.byref(n), C.byref(pad), C.byref(missing))
+        _raise(st, missing.value)
+        return CompressData(out[: n.value], pad.value, huff_tree)
     ptr, n, pad, missing = C.c_void_p(), C.c_size_t(0), C.c_uint8(0), C.c_uint8(0)
     st = L.load().hb_compress_with_tree_u8(ctx.handle, a.ctypes.data, a.size, C.byref(huff_tree.raw),
                                            C.byref(ptr), C.byref(n), C.byref(pad), C.byref(missing))

@@ -54,29 +54,58 @@ def _paths(src: str, dst: str, decompress: bool) -> tuple[str, str]:
     return src, dst
 
 
-def compress_file(src: str, dst: str, block_size: int) -> None:
-    """src/comp.rs:32-74"""
+def _read_pinned(path: str):
+    """The whole file in page-locked memory (hb_host_alloc), read in 64 MiB pieces straight into it: the H2D copy that
+    follows runs at PCIe speed without a second host copy."""
     from . import api
-    data = np.fromfile(src, dtype=np.uint8)
-    if data.size == 0:
-        raise SystemExit("provided empty weights")               # tree_inner.rs:283-285
-    bw = api.ByteWeights()
-    for s in range(0, data.size, block_size):                    # src/comp.rs:161-172
-        bw += api.ByteWeights.threaded_from_bytes(data[s:s + block_size], 12)
-    tree = api.HuffTree.from_weights(bw)
-    cd = api.compress_with_tree(data, tree)
-    with open(dst, "wb") as f:
-        f.write(cd.to_bytes())
+    n = os.path.getsize(path)
+    buf = api.PinnedBuffer(n)
+    view = memoryview(buf.array) if n else memoryview(b"")
+    with open(path, "rb", buffering=0) as f:
+        got = 0
+        while got < n:
+            k = f.readinto(view[got: min(n, got + (64 << 20))])
+            if not k:
+                break
+            got += k
+    if got != n:
+        raise SystemExit(f"short read on {path!r}")
+    return buf
+
+
+def compress_file(src: str, dst: str, block_size: int) -> None:
+    """src/comp.rs:32-74.  Source and stream are staged in pinned host memory; the container header is written first and the
+    stream follows from the pinned buffer without being copied together with it."""
+    from . import api
+    with _read_pinned(src) as inp:
+        data = inp.array
+        if data.size == 0:
+            raise SystemExit("provided empty weights")               # tree_inner.rs:283-285
+        bw = api.ByteWeights()
+        for s in range(0, data.size, block_size):                    # src/comp.rs:161-172
+            bw += api.ByteWeights.threaded_from_bytes(data[s:s + block_size], 12)
+        tree = api.HuffTree.from_weights(bw)
+        with api.PinnedBuffer(data.size + data.size // 4 + 4096) as outp:
+            cd = api.compress_with_tree(data, tree, out=outp.array)
+            header = api.CompressData(np.zeros(1, np.uint8), cd.padding_bits(), tree).to_bytes()[:-1]
+            with open(dst, "wb") as f:
+                f.write(header)                                          # (tree_pad << 4) + data_pad, BE u32 tree bytes, tree
+                f.write(memoryview(cd.comp_bytes()))                     # the stream, straight from pinned memory
 
 
 def decompress_file(src: str, dst: str) -> None:
     """src/comp.rs:79-157"""
     from . import api
-    blob = np.fromfile(src, dtype=np.uint8)
-    if blob.size < 5:
-        raise SystemExit("MissingHeaderInfo")
-    cd = api.CompressData.try_from_bytes(blob)
-    api.decompress(cd).tofile(dst)
+    with _read_pinned(src) as inp:
+        blob = inp.array
+        if blob.size < 5:
+            raise SystemExit("MissingHeaderInfo")
+        cd = api.CompressData.try_from_bytes(blob, copy=False)       # comp_bytes stay a view of the pinned file image
+        bound = cd.comp_bytes().size * 8 // max(1, min(len(c) for c in cd.huff_tree().read_codes().values())) + 64
+        with api.PinnedBuffer(bound) as outp:
+            back = api.decompress(cd, out=outp.array)
+            with open(dst, "wb") as f:
+                f.write(memoryview(back))
 
 
 def main(argv=None) -> int:

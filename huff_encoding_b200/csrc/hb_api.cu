@@ -420,7 +420,8 @@ hb_status ensure_dec_tables(hb_ctx *ctx) {
     }
     tp.root = tree.root;
     tp.n_nodes = n;
-    tp.emit_bits = hb::kEmitBits;
+    tp.emit_bits = tree.max_len <= static_cast<uint32_t>(hb::kEmitBits) ? hb::kEmitBits
+                 : (tree.max_len <= static_cast<uint32_t>(hb::kEmitBitsWide) ? hb::kEmitBitsWide : 0);
     for (int b = 0; b < 256; b++) tp.code_len[b] = tree.has_code[b] ? static_cast<uint8_t>(std::min<uint32_t>(tree.code_len[b], 255)) : 0;
     hb::dec_tables_kernel<<<1, hb::kTabThreads, 0, ctx->stream>>>(tp, ctx->d_dec_tables, ctx->d_emit, ctx->d_code_len, hb::kCntBits);
     ctx->launches++;
@@ -546,17 +547,22 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
 }
 
 // ---------------------------------------------------------------- fused one-kernel decoder (hb_decode_fused.cuh)
+// index width of the emit table for a tree: the regular 12-bit table, or the wide one for codes of 13..14 bits
+int fused_emit_bits(const hb_tree *tree) {
+    return tree->max_len <= static_cast<uint32_t>(hb::kEmitBits) ? hb::kEmitBits : hb::kEmitBitsWide;
+}
+
 // Number of teams per CTA for a tree the fused kernel can serve, 0 if it cannot.
 int fused_teams(const hb_ctx *ctx, const hb_tree *tree) {
     if (!ctx->fused_enabled) return 0;
-    if (tree->max_len > static_cast<uint32_t>(hb::kEmitBits) || tree->n_leaves < 2) return 0;
+    if (tree->max_len > static_cast<uint32_t>(hb::kEmitBitsWide) || tree->n_leaves < 2) return 0;
     // near-fixed-length code sets (all lengths within one bit) resynchronise too slowly for the one speculative entry per
     // chunk the fused kernel cannot repair: leave them to the two-pass decoder and its repair kernel
     if (tree->max_len - tree->min_len < 2) return 0;
     uint32_t coded = 0;
     for (int b = 0; b < 256; b++) coded += tree->has_code[b] ? 1u : 0u;
     if (coded != tree->n_leaves) return 0;                     // duplicate letters (ByteWeights quirk): two-pass decoder
-    const size_t budget = 232448 - hb::fused_shared_bytes();
+    const size_t budget = 232448 - hb::fused_shared_bytes(fused_emit_bits(tree));
     int teams = std::min<int>(hb::kFMaxTeams, static_cast<int>(budget / hb::fused_team_bytes()));
     if (ctx->fused_teams_forced > 0) teams = std::min(teams, ctx->fused_teams_forced);
     return teams;
@@ -601,8 +607,12 @@ hb_status run_fused(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits, uint
     p.out = d_out;
     p.out_cap = out_cap;
     const int grid = static_cast<int>(std::min<uint64_t>(ctx->sm_count, (n_chunks + teams - 1) / teams));
-    const size_t smem = hb::fused_shared_bytes() + static_cast<size_t>(teams) * hb::fused_team_bytes();
-    hb::dec_fused_kernel<<<grid, teams * hb::kFTeam, smem, ctx->stream>>>(p);
+    const int eb = fused_emit_bits(tree);
+    const size_t smem = hb::fused_shared_bytes(eb) + static_cast<size_t>(teams) * hb::fused_team_bytes();
+    if (eb == hb::kEmitBits)
+        hb::dec_fused_kernel<hb::kEmitBits><<<grid, teams * hb::kFTeam, smem, ctx->stream>>>(p);
+    else
+        hb::dec_fused_kernel<hb::kEmitBitsWide><<<grid, teams * hb::kFTeam, smem, ctx->stream>>>(p);
     ctx->launches++;
     HB_CUDA(cudaGetLastError());
     HB_CUDA(cudaMemcpyAsync(ctx->h_fused_result, d_result, sizeof(hb::FusedResult), cudaMemcpyDeviceToHost, ctx->stream));
@@ -748,11 +758,12 @@ hb_status hb_ctx_create(int device, hb_ctx **out) {
         { const char *nw = std::getenv("HB_NO_ENCODE_WARPS"); ctx->enc_warps = !(nw && nw[0] == '1'); }
         HB_CUDA(cudaMalloc(&ctx->d_total_bits, sizeof(unsigned long long)));
         HB_CUDA(cudaMalloc(&ctx->d_dec_tables, sizeof(hb::DecTables)));
-        HB_CUDA(cudaMalloc(&ctx->d_emit, sizeof(uint32_t) << hb::kEmitBits));
+        HB_CUDA(cudaMalloc(&ctx->d_emit, sizeof(uint32_t) << hb::kEmitBitsWide));
         HB_CUDA(cudaMalloc(&ctx->d_code_len, 256));
         HB_CUDA(cudaMalloc(&ctx->d_fused_ctl, 16 + sizeof(hb::FusedResult)));
         HB_CUDA(cudaMallocHost(&ctx->h_fused_result, sizeof(hb::FusedResult)));
-        HB_CUDA(cudaFuncSetAttribute(hb::dec_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        HB_CUDA(cudaFuncSetAttribute(hb::dec_fused_kernel<hb::kEmitBits>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        HB_CUDA(cudaFuncSetAttribute(hb::dec_fused_kernel<hb::kEmitBitsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         { const char *nf = std::getenv("HB_NO_FUSED"); ctx->fused_enabled = !(nf && nf[0] == '1'); }
         { const char *tf = std::getenv("HB_FUSED_TEAMS"); ctx->fused_teams_forced = tf ? std::atoi(tf) : 0; }
         HB_CUDA(cudaMalloc(&ctx->d_fix_enc, 256));

@@ -59,7 +59,9 @@ constexpr int kFHaloAfter = 32;                                // words staged a
 constexpr int kFWinWords = kFHalo + kFChunkWords + kFHaloAfter;
 constexpr int kFWinAlloc = kFWinWords + 4;                     // + look-ahead slack
 constexpr uint32_t kFWinBits = kFWinWords * 32u;
-constexpr int kEmitBits = HB_EMIT_BITS;
+constexpr int kEmitBits = HB_EMIT_BITS;                         // index width of the emit table: trees whose codes fit it ...
+constexpr int kEmitBitsWide = 14;                              // ... and a second kernel instance for codes of up to 14 bits
+                                                               // (64 KiB table, three teams per SM instead of four)
 #ifndef HB_FUSED_LOOKBACK_BITS
 #define HB_FUSED_LOOKBACK_BITS 320       // in-team look-back: a refuted thread costs its whole team (and, through the
 #endif                                   // look-back, every later chunk) a second count, so it is longer than the two-pass one
@@ -72,9 +74,9 @@ constexpr int kFRingWords = 16, kFRingStride = 16;             // 64-byte ring p
                                                                // [k][t], so a lane always hits bank t % 32 wherever it is in its ring
 // letters a thread may decode beyond the end of its last row before it notices: one block of lookups
 constexpr int kFOverrunLetters = 31 + 6 * kFEmitTrips;
-static_assert(kEmitBits <= 13 && kEmitBits >= 8, "emit table index width");
+static_assert(kEmitBits <= 13 && kEmitBits >= 8 && kEmitBitsWide <= 15, "emit table index width (4-bit length field)");
 static_assert(kFHalo * 32 >= HB_LEAD_LOOKBACK_BITS, "the leading look-back must fit the halo");
-static_assert(kFHaloAfter * 32 >= kFOverrunLetters * kEmitBits + 2 * kEmitBits + 96, "the last thread's overrun must fit the halo");
+static_assert(kFHaloAfter * 32 >= kFOverrunLetters * kEmitBitsWide + 2 * kEmitBitsWide + 96, "the last thread's overrun must fit the halo");
 static_assert(31 + 6 * kFEmitTrips <= 4 * kFRingWords - 3, "pending letters + one block must fit the ring");
 
 constexpr uint64_t kDescAgg = 1ull << 62, kDescPrefix = 2ull << 62;
@@ -118,8 +120,8 @@ struct FusedParams {
 __host__ __device__ constexpr size_t fused_team_bytes() {
     return static_cast<size_t>(kFWinAlloc) * 4 + 48 + static_cast<size_t>(kFTeam) * kFRingStride * 4 + kFTeam * 4 + 128;
 }
-__host__ __device__ constexpr size_t fused_shared_bytes() { return (static_cast<size_t>(1) << kEmitBits) * 4 + 256; }
-static_assert(fused_team_bytes() % 64 == 0 && fused_shared_bytes() % 64 == 0 && (kFWinAlloc * 4 + 48) % 64 == 0,
+__host__ __device__ constexpr size_t fused_shared_bytes(int emit_bits) { return (static_cast<size_t>(1) << emit_bits) * 4 + 256; }
+static_assert(fused_team_bytes() % 64 == 0 && fused_shared_bytes(kEmitBits) % 64 == 0 && (kFWinAlloc * 4 + 48) % 64 == 0,
               "64-byte alignment of the team blocks and of the rings");
 
 __device__ __forceinline__ void team_sync(int team) {
@@ -177,15 +179,17 @@ struct FReader {
     }
 };
 
-// byte offset of the emit-table entry for the next kEmitBits bits
+// byte offset of the emit-table entry for the next EB bits
+template <int EB>
 __device__ __forceinline__ uint32_t emit_off(uint32_t x) {
     uint32_t y;
-    asm("and.b32 %0, %1, %2;" : "=r"(y) : "r"(x), "n"(~((1u << (32 - kEmitBits)) - 1u)));
-    return y >> (30 - kEmitBits);
+    asm("and.b32 %0, %1, %2;" : "=r"(y) : "r"(x), "n"(~((1u << (32 - EB)) - 1u)));
+    return y >> (30 - EB);
 }
 
 // Advance from q over whole code words: first code-word start >= q_stop, kEnd32 if a code word does not end at or before
 // q_avail.  `letters` counts the code words passed.  (Phase A and the count pass.)
+template <int EB>
 __device__ __forceinline__ uint32_t fused_run(uint32_t win, uint32_t lut, uint32_t lens, uint32_t q, uint32_t q_stop,
                                               uint32_t q_avail, uint32_t &letters, uint32_t k1 = 1u, uint32_t k4 = 4u) {
     letters = 0;
@@ -196,16 +200,16 @@ __device__ __forceinline__ uint32_t fused_run(uint32_t win, uint32_t lut, uint32
     uint32_t acc = 0;                                      // sum of the entries' top bytes: bits << 4 | count
     const uint32_t q_begin = q;
     const uint32_t lim = min(q_stop, q_avail);
-    if (lim >= 2u * kEmitBits) {
-        const uint32_t last2 = lim - 2 * kEmitBits;        // both lookups of a trip start at or before lim - kEmitBits
+    if (lim >= 2u * EB) {
+        const uint32_t last2 = lim - 2 * EB;        // both lookups of a trip start at or before lim - kEmitBits
 #pragma unroll 1
         while (rd.q <= last2) {
             // two lookups per peek: the 32 peeked bits always hold a second kEmitBits-bit window behind the first
             // entry's <= kEmitBits bits, so one refill test serves both
             const uint32_t x = rd.peek();
-            const uint32_t e1 = lds32(lut + emit_off(x));
+            const uint32_t e1 = lds32(lut + emit_off<EB>(x));
             const uint32_t b1 = e1 >> 28;
-            const uint32_t e2 = lds32(lut + emit_off(x << b1));
+            const uint32_t e2 = lds32(lut + emit_off<EB>(x << b1));
             rd.step_fma(b1 + (e2 >> 28));
             acc += (e1 >> 24) + (e2 >> 24);
         }
@@ -214,7 +218,7 @@ __device__ __forceinline__ uint32_t fused_run(uint32_t win, uint32_t lut, uint32
 #pragma unroll 1
     for (;;) {                                             // the last few letters before q_stop, one at a time
         if (rd.q >= q_stop) { ret = rd.q; break; }
-        const uint32_t e = lds32(lut + emit_off(rd.peek()));
+        const uint32_t e = lds32(lut + emit_off<EB>(rd.peek()));
         const uint32_t len = lds8(lens + (e & 0xFFu));
         if (rd.q + len > q_avail) { ret = kEnd32; break; }
         rd.step(len);
@@ -227,6 +231,7 @@ __device__ __forceinline__ uint32_t fused_run(uint32_t win, uint32_t lut, uint32
 
 // Careful emit (threads near the end of the owned stream range, and the thread with the ragged head of the whole output):
 // letter by letter with every check, straight into registers: 32 letters, one 256-bit store per output row.
+template <int EB>
 __device__ __noinline__ void fused_careful_rows(uint32_t win, uint32_t lut, uint32_t lens, uint32_t entry, uint32_t q_own_end,
                                                 uint32_t q_avail, uint32_t count, uint8_t *out, uintptr_t out_addr, uint64_t D,
                                                 uint64_t out_cap) {
@@ -235,7 +240,7 @@ __device__ __noinline__ void fused_careful_rows(uint32_t win, uint32_t lut, uint
     rd.init(win, entry);
     auto next = [&](uint32_t &letter) -> bool {                // false: no further letter of the owned range exists
         if (rd.q >= q_own_end) return false;
-        const uint32_t e = lds32(lut + emit_off(rd.peek()));
+        const uint32_t e = lds32(lut + emit_off<EB>(rd.peek()));
         letter = e & 0xFFu;
         const uint32_t len = lds8(lens + letter);
         if (rd.q + len > q_avail) return false;
@@ -313,27 +318,28 @@ extern __shared__ __align__(128) uint8_t fused_smem[];
 enum { kMWarp = 0, kMFlag = 8, kMBaseLo = 10, kMBaseHi = 11, kMExit = 13, kMEntry = 14, kMNext = 15,
        kMBar = 16 /* 8 bytes */, kMPrefetched = 18 };
 
+template <int EB>
 __global__ void __launch_bounds__(kFTeam * kFMaxTeams, 1)
 dec_fused_kernel(const FusedParams p) {
     const int team = threadIdx.x / kFTeam, tt = threadIdx.x % kFTeam;
     const int lane = tt & 31;
     uint32_t *s_lut = reinterpret_cast<uint32_t *>(fused_smem);
-    uint8_t *s_lens = fused_smem + (static_cast<size_t>(1) << kEmitBits) * 4;
-    uint8_t *tb = fused_smem + fused_shared_bytes() + team * fused_team_bytes();
+    uint8_t *s_lens = fused_smem + (static_cast<size_t>(1) << EB) * 4;
+    uint8_t *tb = fused_smem + fused_shared_bytes(EB) + team * fused_team_bytes();
     uint32_t *s_win = reinterpret_cast<uint32_t *>(tb);
     uint32_t *s_ring = s_win + kFWinAlloc + 12;             // 64-byte aligned
     uint32_t *s_exit = s_ring + kFTeam * kFRingStride;
     uint32_t *s_misc = s_exit + kFTeam;
 
-    for (int i = threadIdx.x; i < (1 << kEmitBits); i += blockDim.x) s_lut[i] = p.emit[i];
+    for (int i = threadIdx.x; i < (1 << EB); i += blockDim.x) s_lut[i] = p.emit[i];
     for (int i = threadIdx.x; i < 64; i += blockDim.x)
         reinterpret_cast<uint32_t *>(s_lens)[i] = reinterpret_cast<const uint32_t *>(p.code_len)[i];
 
     uint32_t b = smem_addr(fused_smem);
     asm volatile("mov.u32 %0, %0;" : "+r"(b));             // one opaque base register (see hb_decode.cuh)
     const uint32_t a_lut = b;
-    const uint32_t a_lens = b + (1u << kEmitBits) * 4u;
-    const uint32_t a_win = b + static_cast<uint32_t>(fused_shared_bytes() + team * fused_team_bytes());
+    const uint32_t a_lens = b + (1u << EB) * 4u;
+    const uint32_t a_win = b + static_cast<uint32_t>(fused_shared_bytes(EB) + team * fused_team_bytes());
     // ring word k of this thread is at ring_t + k * (4 * kFTeam)
     const uint32_t ring_t = a_win + kFWinAlloc * 4u + 48u + static_cast<uint32_t>(tt) * 4u;
     const uint32_t a_bar = smem_addr(s_misc + kMBar);
@@ -444,7 +450,7 @@ dec_fused_kernel(const FusedParams p) {
                     if (rem) q0 += p.len_gcd - rem;
                 }
                 uint32_t dummy;
-                entry = fused_run(a_win, a_lut, a_lens, q0, q_lo, q_avail, dummy, p.k1, p.k4);
+                entry = fused_run<EB>(a_win, a_lut, a_lens, q0, q_lo, q_avail, dummy, p.k1, p.k4);
             }
         }
 
@@ -453,7 +459,7 @@ dec_fused_kernel(const FusedParams p) {
         bool redo = active;
         for (int round = 0;; round++) {
             if (round > kFTeam + 1) asm volatile("trap;");
-            if (redo) exitq = fused_run(a_win, a_lut, a_lens, entry, q_hi, q_avail, count, p.k1, p.k4);
+            if (redo) exitq = fused_run<EB>(a_win, a_lut, a_lens, entry, q_hi, q_avail, count, p.k1, p.k4);
             s_exit[tt] = exitq;
             if (tt == 0) s_misc[kMFlag] = 0;
             team_sync(team);
@@ -558,11 +564,11 @@ dec_fused_kernel(const FusedParams p) {
             const uint32_t p_end = p0 + count;                                      // row space: my letters are [p0, p_end)
             const uint32_t target = (p_end + 31u) & ~31u;                           // my last row ends here
             // the fast loop may read (target - p_end) + one block of letters past my own: all of it must be real stream
-            const uint32_t reach = q_hi + (kFOverrunLetters + 1) * kEmitBits + 64;
+            const uint32_t reach = q_hi + (kFOverrunLetters + 1) * EB + 64;
             const bool careful = reach > min(q_avail, q_own_end) || (D == 0 && p0 != 0) ||
                                  static_cast<uint64_t>(D - p0) + target > p.out_cap;
             if (careful) {
-                fused_careful_rows(a_win, a_lut, a_lens, entry, q_own_end, q_avail, count, p.out, out_addr, D, p.out_cap);
+                fused_careful_rows<EB>(a_win, a_lut, a_lens, entry, q_own_end, q_avail, count, p.out, out_addr, D, p.out_cap);
                 atomicAdd(&p.result->careful_threads, 1u);
             } else if (target > 32u || p0 == 0) {
                 FReader rd;
@@ -592,9 +598,9 @@ dec_fused_kernel(const FusedParams p) {
 #pragma unroll
                     for (int t2 = 0; t2 < kFEmitTrips; t2++) {
                         const uint32_t x = rd.peek();
-                        const uint32_t e1 = lds32(a_lut + emit_off(x));
+                        const uint32_t e1 = lds32(a_lut + emit_off<EB>(x));
                         const uint32_t b1 = e1 >> 28;
-                        const uint32_t e2 = lds32(a_lut + emit_off(x << b1));
+                        const uint32_t e2 = lds32(a_lut + emit_off<EB>(x << b1));
                         rd.step_fma(b1 + (e2 >> 28));
                         append(e1);
                         append(e2);

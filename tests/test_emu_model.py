@@ -1,0 +1,60 @@
+"""The `-m gpu` parity tests, run WITHOUT a GPU against the CPU execution model of the library (tests/emu).
+
+tests/emu compiles the product's own kernel and host sources (huff_encoding_b200/csrc, untouched; see translate.py) with g++
+against a small model of the CUDA execution model: a fiber per CUDA thread, real barriers and warp collectives, one
+bounds-checked shared-memory arena per CTA, guarded device allocations, the PTX alignment rules of vector and bulk
+accesses.  What runs is the same code path the B200 runs, kernel for kernel and launch for launch -- so indexing, halo,
+barrier, look-back-protocol and host-logic errors show up here, on every CPU run, and not only at the next GPU session.
+The model is test infrastructure: the product never loads it, and nothing measured ever comes from it."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+
+SUITES = ["tests/test_gpu_parity.py", "tests/test_gpu_fused.py", "tests/test_gpu_encode_warps.py", "tests/test_gpu_fuzz.py"]
+# full-size property tests (1 GiB and more): the B200's job
+DESELECT = ["tests/test_gpu_parity.py::test_config1_one_gib_uniform_properties"]
+
+
+@pytest.fixture(scope="module")
+def model_so():
+    import build as emu_build
+    return emu_build.build()
+
+
+def _run(model_so, args, extra_env=None, timeout=3000):
+    env = dict(os.environ, HB_EMU="1", HUFFB200_SO=model_so)
+    env.update(extra_env or {})
+    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + args
+    for d in DESELECT:
+        cmd += ["--deselect", d]
+    return subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+
+
+def test_the_model_exports_the_whole_c_abi(model_so):
+    import ctypes as C
+    from huff_encoding_b200 import _lib as L
+    lib = C.CDLL(model_so)
+    for name, _, _ in L.SYMBOLS:
+        assert hasattr(lib, name), name
+
+
+def test_gpu_parity_suites_pass_under_the_cpu_model(model_so):
+    r = _run(model_so, SUITES + ["-n", "4"], {"HB_EMU_WORKERS": "2"})
+    tail = (r.stdout + r.stderr)[-4000:]
+    assert r.returncode == 0, tail
+    m = re.search(r"(\d+) passed", r.stdout)
+    assert m and int(m.group(1)) >= 130, tail
+    assert "skipped" not in r.stdout.splitlines()[-1], tail          # nothing may be skipped silently
+
+
+def test_decoder_tests_with_few_sms_and_one_resident_cta(model_so):
+    # other interleavings of the chunk tickets and the look-back: 3 SMs, CTAs strictly one after the other
+    r = _run(model_so, ["tests/test_gpu_fused.py", "-k", "fused_path_is_taken or matches_two_pass or wide_table or unaligned"],
+             {"HB_EMU_SMS": "3", "HB_EMU_WORKERS": "1"})
+    assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]

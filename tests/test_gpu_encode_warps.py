@@ -9,6 +9,7 @@ pytestmark = pytest.mark.gpu
 
 from huff_encoding_b200 import datagen as G
 from oracle import oracle as O
+from tests._model import dev, dev_sync, make_engine
 
 
 @pytest.fixture(scope="module")
@@ -24,7 +25,7 @@ def _engine(**env):
     for k, v in env.items():
         os.environ[k] = v
     try:
-        return Engine(0)
+        return make_engine()
     finally:
         for k in env:
             del os.environ[k]
@@ -49,16 +50,16 @@ def test_warp_encoder_equals_region_encoder_with_start_bits():
     new, old = _engine(), _engine(HB_NO_ENCODE_WARPS="1")
     for gen, n in (("zipf", 5_000_011), ("english", 3_000_000), ("uniform", 2_000_001)):
         data = getattr(G, gen)(n)
-        d = torch.from_numpy(data).cuda()
+        d = torch.from_numpy(data).to(dev())
         tree = new.tree_from_weights(np.bincount(data, minlength=256))
         for start_bit in (0, 1, 7, 13, 31):
             outs = []
             for eng in (new, old):
-                out = torch.zeros(n + n // 2 + 64, dtype=torch.uint8, device="cuda")
-                tb = torch.zeros(1, dtype=torch.int64, device="cuda")
+                out = torch.zeros(n + n // 2 + 64, dtype=torch.uint8, device=dev())
+                tb = torch.zeros(1, dtype=torch.int64, device=dev())
                 eng.histogram(d)
                 eng.encode(d, tree, out, start_bit=start_bit, total_bits=tb)
-                torch.cuda.synchronize()
+                dev_sync()
                 bits = int(tb.item())
                 outs.append((bits, out[: (start_bit + bits + 7) // 8].cpu().numpy()))
             assert outs[0][0] == outs[1][0], (gen, start_bit)
@@ -70,16 +71,16 @@ def test_same_address_different_data_is_not_served_from_a_stale_histogram():
     import torch
     eng = _engine()
     n = 3_000_000
-    a = torch.from_numpy(G.english(n, seed=1)).cuda()
+    a = torch.from_numpy(G.english(n, seed=1)).to(dev())
     tree = eng.tree_from_weights(np.bincount(np.concatenate([G.english(n, seed=1), G.english(n, seed=2)]), minlength=256))
-    out = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(n + 64, dtype=torch.uint8, device=dev())
     eng.histogram(a)
     eng.encode(a, tree, out)
-    a.copy_(torch.from_numpy(G.english(n, seed=2)).cuda())     # same address, other letters, no new histogram call
-    out2 = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
-    tb = torch.zeros(1, dtype=torch.int64, device="cuda")
+    a.copy_(torch.from_numpy(G.english(n, seed=2)).to(dev()))     # same address, other letters, no new histogram call
+    out2 = torch.zeros(n + 64, dtype=torch.uint8, device=dev())
+    tb = torch.zeros(1, dtype=torch.int64, device=dev())
     eng.encode(a, tree, out2, total_bits=tb)
-    torch.cuda.synchronize()
+    dev_sync()
     bits = int(tb.item())
     otree = O.tree_from_weights(np.bincount(np.concatenate([G.english(n, seed=1), G.english(n, seed=2)]), minlength=256).astype(np.uint64))
     comp, pad = O.compress_with_tree(G.english(n, seed=2), otree)
@@ -95,11 +96,11 @@ def test_encode_dev_reports_letters_without_a_code():
     tree = eng.tree_from_weights(np.bincount(data, minlength=256))
     bad = data.copy()
     bad[77_777] = 0x01                                        # a letter the tree has no code for
-    d = torch.from_numpy(bad).cuda()
-    out = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+    d = torch.from_numpy(bad).to(dev())
+    out = torch.zeros(n + 64, dtype=torch.uint8, device=dev())
     eng.encode(d, tree, out)
     flag = C.c_uint32(0)
     assert eng.lib.hb_ctx_last_encode_error(eng.ctx.handle, C.byref(flag)) == 0 and flag.value == 1
-    d2 = torch.from_numpy(data).cuda()
+    d2 = torch.from_numpy(data).to(dev())
     eng.encode(d2, tree, out)
     assert eng.lib.hb_ctx_last_encode_error(eng.ctx.handle, C.byref(flag)) == 0 and flag.value == 0

@@ -8,6 +8,7 @@ pytestmark = pytest.mark.gpu
 
 from huff_encoding_b200 import datagen as G
 from oracle import oracle as O
+from tests._model import dev, dev_sync, make_engine
 
 
 @pytest.fixture(scope="module")
@@ -104,11 +105,11 @@ def test_fused_skewed_and_near_uniform_trees(hb):
 def test_fused_device_buffers_unaligned_output_and_capacity(hb):
     import torch
     from huff_encoding_b200.engine import Engine
-    eng = Engine(0)
+    eng = make_engine()
     data = G.zipf(2_345_679)
-    d = torch.from_numpy(data).cuda()
+    d = torch.from_numpy(data).to(dev())
     comp, n, pad, tree = eng.compress(d)
-    base = torch.empty(data.size + 256, dtype=torch.uint8, device="cuda")
+    base = torch.empty(data.size + 256, dtype=torch.uint8, device=dev())
     for off in (0, 1, 7, 32, 45):
         out = base[off: off + data.size + 64]
         out.zero_()
@@ -116,11 +117,11 @@ def test_fused_device_buffers_unaligned_output_and_capacity(hb):
         assert m == data.size and torch.equal(dec[:m], d), off
         assert eng.ctx.last_decode_path()[0] == 1
     # an output buffer of exactly n bytes (no slack behind the last row)
-    exact = torch.empty(data.size, dtype=torch.uint8, device="cuda")
+    exact = torch.empty(data.size, dtype=torch.uint8, device=dev())
     dec, m = eng.decompress(comp, n, pad, tree, out=exact)
     assert m == data.size and torch.equal(dec[:m], d)
     # a buffer that is too small: the needed size is reported and a second call with a larger buffer works
-    small = torch.empty(1000, dtype=torch.uint8, device="cuda")
+    small = torch.empty(1000, dtype=torch.uint8, device=dev())
     dec, m = eng.decompress(comp, n, pad, tree, out=small)
     assert m == data.size and torch.equal(dec[:m], d)
 
@@ -161,4 +162,15 @@ def test_host_api_slab_pipelined_general_decode(hb):
         small = np.empty(n - 1000, dtype=np.uint8)           # too small: the exact size is reported, nothing is lost
         with pytest.raises(Exception):
             hb.decompress(cd, ctx=ctx, out=small)
+    ctx.close()
+
+
+def test_fused_wide_table_for_codes_of_13_and_14_bits(hb):
+    # Zipf(1.5): the rare letters get 13- and 14-bit codes -> the kernel instance with the 14-bit emit table
+    ctx = hb.Context(0)
+    data = G.zipf(5_000_003, s=(15, 10))
+    comp, pad, tree = O.compress(data)
+    longest = max(len(c) for c in tree.codes().values())
+    assert 12 < longest <= 14, longest
+    assert _decode(hb, ctx, data)[0] == 1
     ctx.close()

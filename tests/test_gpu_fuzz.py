@@ -9,6 +9,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 from oracle import oracle as O
+from tests._model import dev, dev_sync, make_engine
 
 BORDERS = [1, 2, 31, 32, 33, 255, 256, 257, 1023, 1024, 1025, 4095, 4096, 4097, 8191, 8192, 8193, 32767, 32768, 32769,
            65535, 65536, 65537, 262143, 262144, 262145]

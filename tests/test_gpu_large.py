@@ -7,6 +7,7 @@ pytestmark = pytest.mark.gpu
 
 from huff_encoding_b200 import datagen as G
 from oracle import oracle as O
+from tests._model import dev, dev_sync, make_engine
 
 
 @pytest.fixture(scope="module")
@@ -14,7 +15,7 @@ def eng():
     from huff_encoding_b200 import build
     build.build()
     from huff_encoding_b200.engine import Engine
-    return Engine(0)
+    return make_engine()
 
 
 def _check_stream_invariants(eng, d, prefix_letters):

@@ -8,6 +8,7 @@ pytestmark = pytest.mark.gpu
 
 from huff_encoding_b200 import datagen as G
 from oracle import oracle as O
+from tests._model import dev, dev_sync, make_engine
 
 
 @pytest.fixture(scope="module")
@@ -21,7 +22,7 @@ def hb():
 @pytest.fixture(scope="module")
 def eng():
     from huff_encoding_b200.engine import Engine
-    return Engine(0)
+    return make_engine()
 
 
 def _first_diff(a, b):

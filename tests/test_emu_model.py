@@ -53,6 +53,12 @@ def test_gpu_parity_suites_pass_under_the_cpu_model(model_so):
     assert "skipped" not in r.stdout.splitlines()[-1], tail          # nothing may be skipped silently
 
 
+def test_single_rank_communicator_under_the_cpu_model(model_so):
+    # hb_comm_init(1 rank) + hb_compress_shard_dev / hb_decompress_shard_dev (no NCCL involved with one rank)
+    r = _run(model_so, ["tests/test_gpu_multi.py", "-k", "single_rank"])
+    assert r.returncode == 0 and "1 passed" in r.stdout, (r.stdout + r.stderr)[-4000:]
+
+
 def test_decoder_tests_with_few_sms_and_one_resident_cta(model_so):
     # other interleavings of the chunk tickets and the look-back: 3 SMs, CTAs strictly one after the other
     r = _run(model_so, ["tests/test_gpu_fused.py", "-k", "fused_path_is_taken or matches_two_pass or wide_table or unaligned"],

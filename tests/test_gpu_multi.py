@@ -68,18 +68,18 @@ def test_two_rank_streams_concatenate_to_the_single_gpu_stream():
 def test_single_rank_comm_matches_compress(tmp_path):
     import torch
     from huff_encoding_b200 import build, datagen as G
-    from huff_encoding_b200.engine import Engine
+    from tests._model import dev, make_engine
     from oracle import oracle as O
     build.build()
-    eng = Engine(0)
+    eng = make_engine()
     eng.comm_init(1, 0, None)
     data = G.zipf(3_000_001)
-    d = torch.from_numpy(data).cuda()
-    comp = torch.zeros(data.size + 64, dtype=torch.uint8, device="cuda")
+    d = torch.from_numpy(data).to(dev())
+    comp = torch.zeros(data.size + 64, dtype=torch.uint8, device=dev())
     lay, tree = eng.compress_shard(d, comp)
     ref, pad, _ = O.compress(data)
     assert lay.start_bit == 0 and lay.bit_offset == 0 and lay.padding_bits == pad and lay.comp_len == ref.size
     assert np.array_equal(comp[: ref.size].cpu().numpy(), ref)
-    out = torch.empty(data.size + 64, dtype=torch.uint8, device="cuda")
+    out = torch.empty(data.size + 64, dtype=torch.uint8, device=dev())
     assert eng.decompress_shard(comp, lay, tree, out) == data.size and torch.equal(out[: data.size], d)
     eng.comm_finalize()

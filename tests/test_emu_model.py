@@ -59,6 +59,16 @@ def test_single_rank_communicator_under_the_cpu_model(model_so):
     assert r.returncode == 0 and "1 passed" in r.stdout, (r.stdout + r.stderr)[-4000:]
 
 
+def test_cpp_mirror_of_the_reference_tests_under_the_cpu_model(model_so, tmp_path):
+    # include/huff_coding.hpp (the C++ mirror of the reference API) with the reference's own test cases, linked against the model
+    exe = str(tmp_path / "test_huff_coding_model")
+    d = os.path.dirname(model_so)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_huff_coding.cpp"),
+                           "-L" + d, "-lhuffb200_emu", "-Wl,-rpath," + d])
+    r = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 def test_decoder_tests_with_few_sms_and_one_resident_cta(model_so):
     # other interleavings of the chunk tickets and the look-back: 3 SMs, CTAs strictly one after the other
     r = _run(model_so, ["tests/test_gpu_fused.py", "-k", "fused_path_is_taken or matches_two_pass or wide_table or unaligned"],

@@ -25,11 +25,17 @@ FLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-pthread", "-DHB_EMU=1"
 def build(force: bool = False) -> str:
     files = translate.translate_tree(OUT)
     deps = files + [os.path.join(HERE, "hb_emu.cpp"), os.path.join(HERE, "include", "hb_emu.h"),
-                    os.path.join(HERE, "include", "cuda_runtime.h"), os.path.join(HERE, "include", "nccl.h"),
+                    os.path.join(HERE, "include", "cuda_runtime.h"), os.path.join(HERE, "include", "nccl.h"), os.path.join(HERE, "nccl_emu.cpp"),
                     os.path.join(ROOT, "include", "huffb200.h"), os.path.abspath(__file__),
                     os.path.join(HERE, "translate.py")]
     if not force and os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
         return SO
+    nccl = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-I", os.path.join(HERE, "include"),
+                           "-o", os.path.join(OUT, "libnccl_emu.so"), os.path.join(HERE, "nccl_emu.cpp")],
+                          capture_output=True, text=True)
+    if nccl.returncode:
+        sys.stderr.write(nccl.stdout + nccl.stderr)
+        raise RuntimeError("g++ failed building libnccl_emu.so")
     srcs = [f for f in files if f.endswith(".cpp")] + [os.path.join(HERE, "hb_emu.cpp")]
     cmd = ["g++"] + FLAGS + ["-I", os.path.join(HERE, "include"), "-I", os.path.join(ROOT, "include"), "-I", OUT,
                              "-o", SO] + srcs + ["-ldl"]

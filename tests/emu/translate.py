@@ -235,6 +235,12 @@ def translate_tree(out_dir: str) -> list[str]:
         if name.endswith((".cu", ".cuh")):
             text = translate(text, path, used)
             text = text.replace('#include "../../include/huffb200.h"', '#include "huffb200.h"')
+            if name == "hb_api.cu":
+                # the model's ranks are threads of one process: NCCL is tests/emu/nccl_emu.cpp, found next to the model
+                if text.count('"libnccl.so.2"') != 2 or text.count('"libnccl.so"') != 1:
+                    raise ValueError("hb_api.cu: the dlopen calls for NCCL are not where translate.py expects them")
+                emu = os.path.join(out_dir, "libnccl_emu.so")
+                text = text.replace('"libnccl.so.2"', f'"{emu}"').replace('"libnccl.so"', f'"{emu}"')
         else:
             text = text.replace('#include "../../include/huffb200.h"', '#include "huffb200.h"')
         dst = os.path.join(out_dir, name[:-3] + ".cpp" if name.endswith(".cu") else name)

@@ -59,6 +59,15 @@ def test_single_rank_communicator_under_the_cpu_model(model_so):
     assert r.returncode == 0 and "1 passed" in r.stdout, (r.stdout + r.stderr)[-4000:]
 
 
+def test_eight_ranks_inside_the_library_under_the_cpu_model(model_so):
+    # hb_comm_init + hb_compress_shard_dev (all-gather of the shard histograms) + hb_decompress_shard_dev with 8 ranks as
+    # threads: concatenated shard streams == the oracle's stream of the concatenated input
+    env = dict(os.environ, HB_EMU="1", HUFFB200_SO=model_so)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "multirank_check.py"), "8"], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and r.stdout.count("ok:") == 3, (r.stdout + r.stderr)[-4000:]
+
+
 def test_cpp_mirror_of_the_reference_tests_under_the_cpu_model(model_so, tmp_path):
     # include/huff_coding.hpp (the C++ mirror of the reference API) with the reference's own test cases, linked against the model
     exe = str(tmp_path / "test_huff_coding_model")

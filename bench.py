@@ -418,6 +418,7 @@ def run_ours(args):
     wd = Watchdog(rank, float(os.environ.get("HB_BENCH_STALL_S", "240")))
     run_ours.watchdog = wd
     eng = Engine(local_rank)
+    dev = eng.device                                  # cuda:<local_rank>
     codec = ShardedCodec(eng, world, rank, dist if world > 1 else None)
     if world > 1:
         # NCCL communicator inside libhuffb200: the timed steps are C calls only.  (NCCL announces its version on the
@@ -507,6 +508,8 @@ def run_ours(args):
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "host_affinity": (f"{len(numa)} CPUs local to the GPU (NVML)" if numa else "not bound"),
         }
+        if args.shrink:
+            line["shrink"] = args.shrink
         wd.line = line
     wd.headline_done = True
     wd.tick()
@@ -556,23 +559,25 @@ def run_ours(args):
                 r["error"] = str(e)
                 sys.stderr.write(f"bench.py rank {rank}: config '{label}' failed: {e}\n")
             configs.append(r)
-            if rank == 0 and "general_frac" not in line and "error" not in r and workload == "zipf" and nbytes == (1 << 30):
+            if rank == 0 and "general_frac" not in line and "error" not in r and workload == "zipf" and nbytes == gib:
                 line["general_frac"] = {"encode": r["frac"]["encode"], "decode": r["frac"]["decode"],
                                         "compress": r["frac"]["compress"], "workload": label}
             ds = cb = ob = None
             torch.cuda.empty_cache()
             wd.tick()
 
-        run_config("1 GiB Zipf(1.2) per GPU (north_star: 1-GPU encode and decode on 1 GiB inputs)", "zipf", 1 << 30, "weak",
+        gib = (1 << 30) >> args.shrink                      # --shrink: control-flow rehearsals only (tests/emu)
+        run_config("1 GiB Zipf(1.2) per GPU (north_star: 1-GPU encode and decode on 1 GiB inputs)", "zipf", gib, "weak",
                    steps=5, with_e2e=True)
         if world == 1:
-            run_config("configs[2]: 4 GiB Zipf(1.2) on one GPU", "zipf", 4 << 30, "weak")
-            run_config("configs[4]: Fibonacci-256, 1 836 311 750 B, 40-bit codes", "fibonacci", 0, "weak", steps=2)
-            run_config("Zipf(1.5), 1 GiB: 1.5 % of the letters have codes of 13 and 14 bits", "zipf15", 1 << 30, "weak")
+            run_config("configs[2]: 4 GiB Zipf(1.2) on one GPU", "zipf", 4 * gib, "weak")
+            if not args.shrink:
+                run_config("configs[4]: Fibonacci-256, 1 836 311 750 B, 40-bit codes", "fibonacci", 0, "weak", steps=2)
+            run_config("Zipf(1.5), 1 GiB: 1.5 % of the letters have codes of 13 and 14 bits", "zipf15", gib, "weak")
         else:
-            run_config(f"configs[2] weak: 4 GiB Zipf(1.2) per GPU x{world}", "zipf", 4 << 30, "weak")
-            run_config(f"configs[2] strong: 4 GiB Zipf(1.2) in total over {world} GPUs", "zipf", (4 << 30) // world, "strong")
-        run_config(f"configs[3]: English-like text, 2 GiB contiguous shard per GPU x{world}", "english", 2 << 30, "weak")
+            run_config(f"configs[2] weak: 4 GiB Zipf(1.2) per GPU x{world}", "zipf", 4 * gib, "weak")
+            run_config(f"configs[2] strong: 4 GiB Zipf(1.2) in total over {world} GPUs", "zipf", 4 * gib // world, "strong")
+        run_config(f"configs[3]: English-like text, 2 GiB contiguous shard per GPU x{world}", "english", 2 * gib, "weak")
 
     wd.done = True
     if rank == 0:
@@ -593,6 +598,9 @@ def main():
     ap.add_argument("--workload", default="uniform", choices=list(WORKLOADS))
     ap.add_argument("--size", type=int, default=1 << 30, help="bytes per GPU")
     ap.add_argument("--no-general", action="store_true", help="skip the secondary configs (zipf / text / fibonacci)")
+    ap.add_argument("--shrink", type=int, default=0,
+                    help="divide the secondary configs' sizes by 2^K and skip Fibonacci: rehearsals of the control flow only "
+                         "(the line then carries \"shrink\": K and is no measurement of the named configs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -1,0 +1,84 @@
+"""TEST INFRASTRUCTURE.  A rehearsal of bench.py's control flow (N = 1) without a GPU: the library is the CPU model
+(HUFFB200_SO), the few torch.cuda entry points bench.py touches are stood in for, sizes are shrunk.  What it checks is that
+the script runs from argument parsing to the one JSON line -- every key access, every branch of the secondary configs -- not
+a single number: times measured here are meaningless and the line says so ("shrink").
+usage: HB_EMU=1 HUFFB200_SO=.../libhuffb200_emu.so python tests/emu/bench_dryrun.py [bench.py arguments]"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+assert os.environ.get("HB_EMU") == "1", "rehearsal only: needs the CPU model of the library"
+
+
+class _Event:
+    def __init__(self, enable_timing=True):
+        self.t = None
+
+    def record(self, stream=None):
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other):
+        return (other.t - self.t) * 1e3
+
+
+class _StreamCtx:
+    def __init__(self, stream):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+class _Stream:
+    def synchronize(self):
+        pass
+
+
+torch.cuda.is_available = lambda: True
+torch.cuda.set_device = lambda d: None
+torch.cuda.synchronize = lambda *a: None
+torch.cuda.empty_cache = lambda: None
+torch.cuda.Event = _Event
+torch.cuda.stream = _StreamCtx
+_empty = torch.empty
+torch.empty = lambda *a, pin_memory=False, **k: _empty(*a, **k)
+
+import huff_encoding_b200.engine as engine_mod  # noqa: E402
+from tests.emu.model_engine import ModelEngine  # noqa: E402
+
+
+class _Engine(ModelEngine):
+    def __init__(self, device=None):
+        super().__init__()
+        self._stream = _Stream()
+
+    def _event(self):
+        return _Event()
+
+
+engine_mod.Engine = _Engine
+
+import huff_encoding_b200.sharded as sharded_mod  # noqa: E402
+
+
+def _codec_event(self):
+    ev = _Event()
+    ev.record()
+    return ev
+
+
+sharded_mod.ShardedCodec._event = _codec_event
+
+import bench  # noqa: E402
+
+if __name__ == "__main__":
+    sys.argv = ["bench.py"] + sys.argv[1:]
+    sys.exit(bench.main())

@@ -68,6 +68,27 @@ def test_eight_ranks_inside_the_library_under_the_cpu_model(model_so):
     assert r.returncode == 0 and r.stdout.count("ok:") == 3, (r.stdout + r.stderr)[-4000:]
 
 
+def test_bench_py_rehearsal_prints_one_json_line_with_every_key(model_so):
+    # bench.py from argument parsing to its JSON line (N = 1), library = CPU model, sizes shrunk 256 x: a rehearsal of the
+    # control flow the driver runs at round end -- no number in that line means anything
+    import json
+    env = dict(os.environ, HB_EMU="1", HUFFB200_SO=model_so)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "bench_dryrun.py"), "--size", str(4 << 20),
+                        "--steps", "4", "--shrink", "8"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks",
+                "cold_tree_ms_per_step", "warm_tree_ms_per_step", "general_frac", "configs", "shrink"):
+        assert key in d, key
+    assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["roofline"]["traffic"] is None   # (no capture at this size)
+    assert len(d["configs"]) == 4 and not any("error" in c for c in d["configs"]), d["configs"]
+    assert [c["decoder"] for c in d["configs"]] == ["fused one-pass"] * 4
+    assert "e2e" in d["configs"][0]
+
+
 def test_cpp_mirror_of_the_reference_tests_under_the_cpu_model(model_so, tmp_path):
     # include/huff_coding.hpp (the C++ mirror of the reference API) with the reference's own test cases, linked against the model
     exe = str(tmp_path / "test_huff_coding_model")

@@ -124,6 +124,9 @@ def load() -> C.CDLL:
             raise ImportError(f"{SO_PATH} is missing: build it with `python -m huff_encoding_b200.build` "
                               "(there is no CPU fallback)")
         L = C.CDLL(SO_PATH)
+        if hasattr(L, "hb_emu_is_model") and os.environ.get("HB_EMU") != "1":
+            # tests/emu builds a CPU model of this library for the test suite; it must never stand in for the product
+            raise ImportError(f"{SO_PATH} is the CPU test model of libhuffb200, not the library (there is no CPU fallback)")
         for name, restype, argtypes in SYMBOLS:
             fn = getattr(L, name)          # AttributeError here = the .so does not export what the header declares
             fn.restype = restype

@@ -104,3 +104,11 @@ def test_decoder_tests_with_few_sms_and_one_resident_cta(model_so):
     r = _run(model_so, ["tests/test_gpu_fused.py", "-k", "fused_path_is_taken or matches_two_pass or wide_table or unaligned"],
              {"HB_EMU_SMS": "3", "HB_EMU_WORKERS": "1"})
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
+
+
+def test_the_product_refuses_to_load_the_model_outside_a_test_run(model_so):
+    env = dict(os.environ, HUFFB200_SO=model_so)
+    env.pop("HB_EMU", None)
+    r = subprocess.run([sys.executable, "-c", "import huff_encoding_b200 as hb; hb.compress(b'abc')"], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "not the library" in r.stderr

@@ -113,10 +113,39 @@ void switch_to(Cta *c, unsigned next) {
     hb_emu_switch(&c->fibers[me].sp, c->fibers[next].sp);
 }
 
-// next runnable fiber after `from` (round robin); n if there is none
+// HB_EMU_ORDER: the order in which the threads of a CTA get their turns.  Code that is correct under the CUDA memory
+// model gives the same result under every order; code that leans on an order (a missing barrier or __syncwarp) does not.
+//   up (default): round robin, ascending thread index   down: descending   random[:seed]: a random runnable thread
+int order_mode() {
+    static const int m = [] {
+        const char *e = getenv("HB_EMU_ORDER");
+        if (!e || !strncmp(e, "up", 2)) return 0;
+        if (!strncmp(e, "down", 4)) return 1;
+        if (!strncmp(e, "random", 6)) return 2;
+        return 0;
+    }();
+    return m;
+}
+uint64_t &rng_state() {
+    static thread_local uint64_t s = [] {
+        const char *e = getenv("HB_EMU_ORDER");
+        const char *colon = e ? strchr(e, ':') : nullptr;
+        return colon ? strtoull(colon + 1, nullptr, 10) * 2654435761ull + 1 : 88172645463325252ull;
+    }();
+    return s;
+}
+unsigned rnd(unsigned n) {
+    uint64_t &x = rng_state();
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    return static_cast<unsigned>((x >> 11) % n);
+}
+
+// next runnable fiber after `from`; n if there is none
 unsigned next_runnable(Cta *c, unsigned from) {
+    const int mode = order_mode();
+    if (mode == 2) from = rnd(c->n);
     for (unsigned k = 1; k <= c->n; k++) {
-        const unsigned i = (from + k) % c->n;
+        const unsigned i = mode == 1 ? (from + c->n - k) % c->n : (from + k) % c->n;
         if (!c->fibers[i].done) return i;
     }
     return c->n;
@@ -209,9 +238,9 @@ void run_cta(Cta *c, Dim3 bid, Dim3 block, Dim3 grid, size_t dyn_bytes, const ch
     }
     c->spins = 0;
     c->last_progress = std::chrono::steady_clock::now();
-    c->cur = 0;
-    g_thread = &c->fibers[0].t;
-    hb_emu_switch(&c->main_sp, c->fibers[0].sp);
+    c->cur = order_mode() == 1 ? n - 1 : (order_mode() == 2 ? rnd(n) : 0);
+    g_thread = &c->fibers[c->cur].t;
+    hb_emu_switch(&c->main_sp, c->fibers[c->cur].sp);
     g_thread = nullptr;
     if (c->live) die("kernel returned to the scheduler with live threads");
 }

@@ -70,7 +70,9 @@ struct Fiber {
     void *sp = nullptr;
     bool done = false;
 };
+struct PendingCopy { uint32_t dst; const void *src; uint32_t bytes, bar; };
 struct Cta {                               // per worker thread, reused CTA after CTA
+    std::vector<PendingCopy> pending;      // bulk copies issued but not yet landed (HB_EMU_BULK=lazy)
     std::vector<Fiber> fibers;
     std::vector<uint8_t *> stacks;         // kMaxThreads guarded stacks, allocated once
     unsigned n = 0, live = 0, cur = 0;
@@ -213,6 +215,7 @@ void run_cta(Cta *c, Dim3 bid, Dim3 block, Dim3 grid, size_t dyn_bytes, const ch
     memset(c->arena, 0xA5, need);                               // shared memory starts out undefined
     c->static_top = 0;
     c->static_sites.clear();
+    c->pending.clear();
     c->n = c->live = n;
     c->body = &body;
     c->name = name;
@@ -352,6 +355,46 @@ uint64_t warp_reduce_or(uint64_t v) {
 }
 
 void trap(const char *why) { die("trap: %s", why); }
+
+static bool bulk_lazy() {
+    static const bool v = [] { const char *e = getenv("HB_EMU_BULK"); return e && !strncmp(e, "lazy", 4); }();
+    return v;
+}
+static void land(Cta *c, const PendingCopy &p) {
+    memcpy(c->arena + p.dst, p.src, p.bytes);
+    uint64_t ph;
+    memcpy(&ph, c->arena + p.bar, 8);
+    ph++;                                                       // complete_tx of all expected bytes: the phase ends
+    memcpy(c->arena + p.bar, &ph, 8);
+}
+void mbar_init(uint32_t bar) {
+    smem_check(bar, 8, "mbarrier.init");
+    const uint64_t z = 0;
+    memcpy(g_cta->arena + bar, &z, 8);
+}
+void bulk_copy(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    Cta *c = g_cta;
+    if ((dst & 15u) || (reinterpret_cast<uintptr_t>(src) & 15) || (bytes & 15u)) trap("cp.async.bulk: addresses and size must be multiples of 16");
+    smem_check(bar, 8, "cp.async.bulk mbarrier");
+    if (static_cast<size_t>(dst) + bytes > c->arena_size) trap("cp.async.bulk: destination beyond the CTA's shared memory");
+    const PendingCopy p{dst, src, bytes, bar};
+    if (bulk_lazy()) c->pending.push_back(p);
+    else land(c, p);
+}
+void mbar_wait(uint32_t bar, uint32_t parity) {
+    Cta *c = g_cta;
+    smem_check(bar, 8, "mbarrier.try_wait");
+    for (size_t i = 0; i < c->pending.size();) {                // lazy copies land now, at the last possible moment
+        if (c->pending[i].bar == bar) { land(c, c->pending[i]); c->pending.erase(c->pending.begin() + i); }
+        else i++;
+    }
+    for (;;) {
+        uint64_t ph;
+        memcpy(&ph, c->arena + bar, 8);
+        if ((ph & 1u) != parity) break;
+        yield();
+    }
+}
 
 uint8_t *smem_base() { return g_cta->arena; }
 size_t smem_size() { return g_cta->arena_size; }

@@ -53,4 +53,11 @@ uint32_t warp_ballot(int pred);
 uint64_t warp_reduce_or(uint64_t v);
 [[noreturn]] void trap(const char *why);
 
+// ---- mbarrier + 1-D bulk copy global -> shared.  The 8 bytes at `bar` hold the phase counter.  HB_EMU_BULK=eager (default):
+//      the copy lands when it is issued; lazy: it lands only when somebody waits on its barrier -- the two ends of what the
+//      hardware may do, so a read of the destination before the wait (or a write to it after the issue) shows as a difference
+void mbar_init(uint32_t bar);
+void mbar_wait(uint32_t bar, uint32_t parity);
+void bulk_copy(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar);
+
 }  // namespace hb_emu

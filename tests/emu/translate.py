@@ -52,16 +52,11 @@ PTX_HELPERS = {
     "step_fma": "const uint32_t qn = q + bits; const uint32_t r = (qn ^ q) & 32u; "
                 "if (r) { w0 = w1 * k1; w1 = w2 * k1; w2 = lds32(wa); wa = k4 * k1 + wa; } q = qn;",
     "emit_off": "const uint32_t y = x & ~((1u << (32 - EB)) - 1u); return y >> (30 - EB);",
-    # mbarrier model: the 8 bytes hold the phase counter; a bulk copy completes at once and ends the phase
-    "mbar_init": f'hb_emu::smem_check(bar, 8, "mbarrier.init"); (void)count; const uint64_t z = 0; memcpy({_SM} + bar, &z, 8);',
+    # mbarrier + bulk copy: hb_emu.cpp (eager or lazy landing of the bytes)
+    "mbar_init": "(void)count; hb_emu::mbar_init(bar);",
     "mbar_expect_tx": 'hb_emu::smem_check(bar, 8, "mbarrier.arrive.expect_tx"); (void)bytes;',
-    "mbar_wait": f'hb_emu::smem_check(bar, 8, "mbarrier.try_wait"); for (;;) {{ uint64_t ph; memcpy(&ph, {_SM} + bar, 8); '
-                 "if ((ph & 1u) != parity) break; hb_emu::yield(); }",
-    "bulk_g2s": 'if ((dst & 15u) || (reinterpret_cast<uintptr_t>(src) & 15) || (bytes & 15u)) '
-                'hb_emu::trap("cp.async.bulk: addresses and size must be multiples of 16"); '
-                f'hb_emu::smem_check(dst, 16, "cp.async.bulk dst"); if (static_cast<size_t>(dst) + bytes > hb_emu::smem_size()) '
-                'hb_emu::trap("cp.async.bulk: destination beyond the CTA\'s shared memory"); '
-                f"memcpy({_SM} + dst, src, bytes); uint64_t ph; memcpy(&ph, {_SM} + bar, 8); ph++; memcpy({_SM} + bar, &ph, 8);",
+    "mbar_wait": "hb_emu::mbar_wait(bar, parity);",
+    "bulk_g2s": "hb_emu::bulk_copy(dst, src, bytes, bar);",
 }
 
 # exact inline statements (whitespace-normalised) -> C++

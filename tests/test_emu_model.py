@@ -101,9 +101,10 @@ def test_cpp_mirror_of_the_reference_tests_under_the_cpu_model(model_so, tmp_pat
 
 def test_decoder_tests_with_few_sms_and_one_resident_cta(model_so):
     # other interleavings: 3 SMs, CTAs strictly one after the other, and the threads of a CTA taking their turns in
-    # DESCENDING order (code that leans on the ascending order -- a missing barrier or __syncwarp -- gives other results)
+    # DESCENDING order (code that leans on the ascending order -- a missing barrier or __syncwarp -- gives other results),
+    # bulk copies landing only when their mbarrier is waited on (a read of the window before the wait would see stale bytes)
     r = _run(model_so, ["tests/test_gpu_fused.py", "-k", "fused_path_is_taken or matches_two_pass or wide_table or unaligned"],
-             {"HB_EMU_SMS": "3", "HB_EMU_WORKERS": "1", "HB_EMU_ORDER": "down"})
+             {"HB_EMU_SMS": "3", "HB_EMU_WORKERS": "1", "HB_EMU_ORDER": "down", "HB_EMU_BULK": "lazy"})
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
 
 

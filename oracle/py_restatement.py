@@ -245,3 +245,93 @@ def decompress(comp: bytes, padding_bits: int, root: Branch) -> bytes:
                 out.append(cur.letter)
                 cur = root
     return bytes(out)
+
+
+# ---------------------------------------------------------------- container format (independent of huff_oracle.c)
+class FromBinError(Exception):
+    """tree_inner.rs:673-700"""
+
+
+class FromBytesError(Exception):
+    """comp.rs:531-554 (CompressedDataFromBytesError)"""
+
+
+class Panic(Exception):
+    """a reference panic!()"""
+
+
+def try_from_bin(bits: str) -> Branch:
+    """tree_inner.rs:522-604, transcribed as the reference writes it: a recursive descent over an iterator of bits.
+    `bits` is a '0'/'1' string (the BitVec)."""
+    import sys
+    sys.setrecursionlimit(max(sys.getrecursionlimit(), 20000))
+    it = iter(bits)
+
+    def read_branch() -> Branch:
+        bit = next(it, None)
+        if bit is None:                                           # :531-536
+            raise FromBinError("Provided BitVec is too small for an encoded HuffTree")
+        if bit == "1":                                            # :538-546 joint branch: left first, then right
+            left = read_branch()
+            right = read_branch()
+            return Branch(None, 0, (left, right))
+        letter_bits = [b for _, b in zip(range(8), it)]           # :556 bits.take(size_of_bits::<u8>())
+        if len(letter_bits) != 8:                                 # :557-561
+            raise FromBinError("Provided BitVec is too small for an encoded HuffTree")
+        byte, bit_ptr = 0, 7
+        for b in letter_bits:                                     # :562-570
+            byte |= int(b) << bit_ptr
+            bit_ptr -= 1
+        return Branch(byte, 0)
+
+    root = read_branch()
+    if next(it, None) is not None:                                # :587-591
+        raise FromBinError("Provided BitVec is too big for an encoded HuffTree")
+    if root.has_children():                                       # :595-600
+        _set_codes(root, None)
+    else:
+        root.code = "0"
+    return root
+
+
+def to_bytes(comp: bytes, padding_bits: int, root: Branch) -> bytes:
+    """comp.rs:279-300"""
+    tree_bin = as_bin(root)
+    tree_pad = (8 - len(tree_bin) % 8) % 8                        # utils.rs:37-40 calc_padding_bits
+    tree_bytes_len = (len(tree_bin) + tree_pad) // 8
+    padded = tree_bin + "0" * tree_pad                            # BitVec::into_vec: dead bits are zero
+    out = bytearray([(tree_pad << 4) + padding_bits])
+    out += tree_bytes_len.to_bytes(4, "big")
+    out += bytes(int(padded[i:i + 8], 2) for i in range(0, len(padded), 8))
+    out += bytes(comp)
+    return bytes(out)
+
+
+def try_from_bytes(blob: bytes):
+    """comp.rs:128-184 -> (comp_bytes, padding_bits, root); FromBytesError for its Err values, Panic for its panics
+    (tree length below 2, and CompressData::new's invariants, comp.rs:56-61)."""
+    blob = bytes(blob)
+    if len(blob) < 1:                                             # :143 bytes.get(0)
+        raise FromBytesError("slice is empty")
+    tree_padding_bits = blob[0] >> 4
+    data_padding_bits = blob[0] & 0b0000_1111
+    if len(blob) < 5:                                             # :148-152 bytes.get(1..5)
+        raise FromBytesError("slice too short to read tree length")
+    tree_len = int.from_bytes(blob[1:5], "big")
+    if tree_len < 2:                                              # :153-155
+        raise Panic("stored tree length must be at least 2")
+    if 5 + tree_len > len(blob):                                  # :160 bytes.get(5..5 + tree_len)
+        raise FromBytesError("slice too short to read tree")
+    bits = "".join(format(b, "08b") for b in blob[5:5 + tree_len])
+    for _ in range(tree_padding_bits):                            # :163 b.pop() (None on an empty vector)
+        bits = bits[:-1]
+    try:
+        root = try_from_bin(bits)
+    except FromBinError:
+        raise FromBytesError("invalid tree in slice") from None   # :167-177
+    comp = blob[5 + tree_len:]                                    # :180 (an empty tail is Some(&[]))
+    if len(comp) == 0:                                            # comp.rs:56-58
+        raise Panic("provided comp_bytes are empty")
+    if data_padding_bits > 7:                                     # comp.rs:59-61
+        raise Panic("padding bits cannot be larger than 7")
+    return comp, data_padding_bits, root

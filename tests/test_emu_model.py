@@ -89,6 +89,16 @@ def test_bench_py_rehearsal_prints_one_json_line_with_every_key(model_so):
     assert "e2e" in d["configs"][0]
 
 
+def test_sharded_codec_over_gloo_with_the_real_kernels_under_the_cpu_model(model_so):
+    # tests/test_sharded_gloo.py (2-4 processes, gloo) with the model engine instead of the oracle-backed one: the Python
+    # orchestration (all-gather of histograms, shard plan, start-bit encode, byte-sharded speculative decode with the
+    # neighbour check) over the library's own kernels
+    env = dict(os.environ, HB_EMU="1", HUFFB200_SO=model_so, HB_EMU_WORKERS="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "tests/test_sharded_gloo.py"], cwd=ROOT,
+                       env=env, capture_output=True, text=True, timeout=2400)
+    assert r.returncode == 0 and "7 passed" in r.stdout, (r.stdout + r.stderr)[-4000:]
+
+
 def test_cpp_mirror_of_the_reference_tests_under_the_cpu_model(model_so, tmp_path):
     # include/huff_coding.hpp (the C++ mirror of the reference API) with the reference's own test cases, linked against the model
     exe = str(tmp_path / "test_huff_coding_model")

@@ -93,6 +93,15 @@ class OracleEngine:
         out[: self._last.size] = torch.from_numpy(self._last)
 
 
+def _engine():
+    """The oracle-backed engine (host logic only), or -- under tests/emu (HB_EMU=1, see tests/test_emu_model.py) -- the engine
+    over the CPU model of the library: the same orchestration with the real kernels' code."""
+    if os.environ.get("HB_EMU") == "1":
+        from tests.emu.model_engine import ModelEngine
+        return ModelEngine()
+    return OracleEngine()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -110,7 +119,7 @@ def _worker(rank, world, port, kind, n_total, q):
         per = n_total // world
         lo, hi = rank * per, (n_total if rank == world - 1 else (rank + 1) * per)
         shard = torch.from_numpy(full[lo:hi].copy())
-        codec = ShardedCodec(OracleEngine(), world, rank, dist)
+        codec = ShardedCodec(_engine(), world, rank, dist)
         comp_buf = torch.zeros(shard.numel() * 2 + 64, dtype=torch.uint8)
         info = codec.compress(shard, comp_buf)
 
@@ -149,8 +158,12 @@ def _worker(rank, world, port, kind, n_total, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,kind,n", [(2, "english", 60_001), (2, "zipf", 50_003), (3, "uniform", 30_000),
-                                          (2, "uniform", 4096)])
+CASES = [(2, "english", 60_001), (2, "zipf", 50_003), (3, "uniform", 30_000), (2, "uniform", 4096)]
+if os.environ.get("HB_EMU") == "1":          # real kernels (CPU model): sizes that span many chunks and sub-regions
+    CASES += [(2, "zipf", 3_000_001), (3, "english", 2_000_003), (4, "zipf", 1_234_567)]
+
+
+@pytest.mark.parametrize("world,kind,n", CASES)
 def test_sharded_codec_gloo(world, kind, n):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

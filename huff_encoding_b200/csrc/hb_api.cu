@@ -157,6 +157,8 @@ struct hb_ctx {
     bool fused_enabled = true;           // HB_NO_FUSED=1: always take the two-pass decoder
     int fused_teams_forced = 0;                  // HB_FUSED_TEAMS: cap on the teams per CTA (A/B measurements)
     uint32_t last_fused = 0;             // 1: the last decompress ran the fused kernel, 2: it was refuted and redone two-pass
+    uint64_t refuted_codes[4] = {0, 0, 0, 0};    // code sets whose speculation was refuted lately: straight to two-pass
+    int refuted_next = 0;
     uint32_t last_fused_slow_chunks = 0;
     hb_tree dec_tree_cached;
     bool dec_tree_valid = false;         // dec_tree_cached / dec_fixed_len describe the last tree seen
@@ -552,6 +554,17 @@ int fused_emit_bits(const hb_tree *tree) {
     return tree->max_len <= static_cast<uint32_t>(hb::kEmitBits) ? hb::kEmitBits : hb::kEmitBitsWide;
 }
 
+// FNV-1a over the code lengths: what decides how fast a code set resynchronises
+uint64_t code_set_hash(const hb_tree *tree) {
+    uint64_t h = 1469598103934665603ull;
+    for (int b = 0; b < 256; b++) {
+        const uint64_t v = tree->has_code[b] ? tree->code_len[b] : 0xFFFFu;
+        h = (h ^ (v & 0xFF)) * 1099511628211ull;
+        h = (h ^ (v >> 8)) * 1099511628211ull;
+    }
+    return h ? h : 1;
+}
+
 // Number of teams per CTA for a tree the fused kernel can serve, 0 if it cannot.
 int fused_teams(const hb_ctx *ctx, const hb_tree *tree) {
     if (!ctx->fused_enabled) return 0;
@@ -562,10 +575,19 @@ int fused_teams(const hb_ctx *ctx, const hb_tree *tree) {
     uint32_t coded = 0;
     for (int b = 0; b < 256; b++) coded += tree->has_code[b] ? 1u : 0u;
     if (coded != tree->n_leaves) return 0;                     // duplicate letters (ByteWeights quirk): two-pass decoder
+    const uint64_t h = code_set_hash(tree);
+    for (uint64_t r : ctx->refuted_codes)
+        if (r == h) return 0;                                  // refuted lately: this code set resynchronises too slowly
     const size_t budget = 232448 - hb::fused_shared_bytes(fused_emit_bits(tree));
     int teams = std::min<int>(hb::kFMaxTeams, static_cast<int>(budget / hb::fused_team_bytes()));
     if (ctx->fused_teams_forced > 0) teams = std::min(teams, ctx->fused_teams_forced);
     return teams;
+}
+
+// slowly resynchronising code set: the next streams of this code set skip the speculative attempt
+void note_refuted(hb_ctx *ctx, const hb_tree *tree) {
+    ctx->refuted_codes[ctx->refuted_next] = code_set_hash(tree);
+    ctx->refuted_next = (ctx->refuted_next + 1) % 4;
 }
 
 // Runs the fused kernel.  *refuted = true: a chunk's speculative entry was wrong (or the kernel cannot serve this call) and
@@ -681,6 +703,7 @@ hb_status decode_range(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits, u
             return HB_OK;
         }
         ctx->last_fused = 2;                                   // fall through: exact two-pass decode (with repair)
+        if (refuted) note_refuted(ctx, tree);
     }
     info->entry_bit = entry_bit;
     HB_TRY(run_count_pass(ctx, d_buf, avail_bits, own_begin, own_end, entry_bit, stream_bit0, tree, info));
@@ -1211,6 +1234,7 @@ static hb_status decompress_host_slabs(hb_ctx *ctx, const uint8_t *comp, size_t 
             rc = run_fused(ctx, ctx->stage_in.p, total_bits, std::max<uint64_t>(own_begin, std::min(entry, own_end)), own_end,
                            entry, 0, tree, teams, ctx->stage_out.p + base, dev_cap - base, &info, &refuted);
             if (rc != HB_OK) break;
+            if (refuted) note_refuted(ctx, tree);
             if (refuted || base + info.n_letters > cap) { rc = HB_ERR_CAPACITY; break; }     // -> unpipelined path
             const size_t n_k = static_cast<size_t>(info.n_letters);
             if (n_k) HB_CUDA(cudaMemcpyAsync(dst + base, ctx->stage_out.p + base, n_k, cudaMemcpyDeviceToHost, ctx->s_d2h));

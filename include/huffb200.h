@@ -169,7 +169,10 @@ hb_status hb_compress_u8_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, int o
                              uint8_t *d_out, size_t out_cap, size_t *comp_len, uint8_t *padding_bits);
 /* decompress() on device buffers.  Decodes the bits [first_bit, total_bits) of d_comp where
  * total_bits = 8 * comp_len - padding_bits; d_comp must be readable up to comp_len rounded up to 16 bytes.
- * If out_cap is too small returns HB_ERR_CAPACITY with *out_n = needed letters (nothing written). */
+ * If out_cap is too small returns HB_ERR_CAPACITY with *out_n = needed letters.  d_out[0 .. out_cap) is the decoder's to
+ * use: on success the first *out_n bytes are the letters and the bytes behind them are UNDEFINED (the one-pass decoder
+ * writes whole 32-byte rows and, when its speculation is refuted, a discarded attempt may have touched any of them);
+ * with HB_ERR_CAPACITY the whole buffer is undefined.  Nothing outside [d_out, d_out + out_cap) is ever written. */
 hb_status hb_decompress_u8_dev(hb_ctx *ctx, const uint8_t *d_comp, size_t comp_len, uint8_t padding_bits,
                                const hb_tree *tree, uint8_t *d_out, size_t out_cap, size_t *out_n);
 
@@ -191,7 +194,8 @@ hb_status hb_decode_write_dev(hb_ctx *ctx, uint8_t *d_out, size_t out_cap);
 /* Count + write in one call for a shard whose first code-word start is KNOWN (info->entry_bit >= 0 on entry), e.g. the
  * shards hb_encode_u8_dev produced (entry = start_bit): takes the one-pass fused decoder (every code word decoded once,
  * stream read once) when the tree allows it, else the two calls above.  HB_ERR_CAPACITY reports info->n_letters and
- * leaves the count state for hb_decode_write_dev. */
+ * leaves the count state for hb_decode_write_dev.  d_out[0 .. out_cap): as for hb_decompress_u8_dev (bytes behind the
+ * letters are undefined; nothing outside the buffer is written). */
 hb_status hb_decode_shard_dev(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits, uint64_t own_begin,
                               uint64_t own_end, uint64_t stream_bit0, const hb_tree *tree, hb_shard_info *info,
                               uint8_t *d_out, size_t out_cap);

@@ -83,8 +83,13 @@ def test_fused_dense_and_sparse_regions(hb):
 
 def test_fused_refuted_speculation_falls_back(hb):
     ctx = _ctx_with(hb, HB_DEBUG_SPOIL_SPECULATION="1")
-    path, _ = _decode(hb, ctx, G.zipf(3_000_017))
+    data = G.zipf(3_000_017)
+    path, _ = _decode(hb, ctx, data)
     assert path == 2
+    # the context remembers the code set: its next stream goes straight to the two-pass decoder (no second lost attempt) ...
+    assert _decode(hb, ctx, data)[0] == 0
+    # ... while another code set still gets its attempt
+    assert _decode(hb, ctx, G.english(1_000_003))[0] == 2
     ctx.close()
 
 

@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE.  A rehearsal of bench.py's control flow (N = 1) without a GPU: the library is the CPU model
 (HUFFB200_SO), the few torch.cuda entry points bench.py touches are stood in for, sizes are shrunk.  What it checks is that
 the script runs from argument parsing to the one JSON line -- every key access, every branch of the secondary configs -- not
-a single number: times measured here are meaningless and the line says so ("shrink").
+a single number: times measured here are meaningless and the line says so ("shrink").  Under torchrun (N > 1) the process
+group is gloo and the library's communicator is the NCCL model of tests/emu (shared memory between the rank processes).
 usage: HB_EMU=1 HUFFB200_SO=.../libhuffb200_emu.so python tests/emu/bench_dryrun.py [bench.py arguments]"""
 import os
 import sys
@@ -76,6 +77,28 @@ def _codec_event(self):
 
 
 sharded_mod.ShardedCodec._event = _codec_event
+
+# fault injection (tests of bench.py's containment): HB_DRYRUN_FAIL="<rank>:<letters>" makes that rank's first round trip over
+# an input of that many letters raise AFTER its collective, like a status returned by the decoder
+_fail = os.environ.get("HB_DRYRUN_FAIL")
+if _fail:
+    _fail_rank, _fail_size = (int(x) for x in _fail.split(":"))
+    _real_round_trip = sharded_mod.ShardedCodec.round_trip
+    _fired = []
+
+    def _round_trip(self, data, comp_buf, out_buf, want_events=False):
+        r = _real_round_trip(self, data, comp_buf, out_buf, want_events)
+        if self.rank == _fail_rank and data.numel() == _fail_size and not _fired:
+            _fired.append(1)
+            raise RuntimeError("libhuffb200: buffer too small (status 5) [injected]")
+        return r
+
+    sharded_mod.ShardedCodec.round_trip = _round_trip
+
+import torch.distributed as dist  # noqa: E402
+
+_init_pg = dist.init_process_group
+dist.init_process_group = lambda backend=None, **kw: _init_pg("gloo")          # N > 1: gloo instead of NCCL
 
 import bench  # noqa: E402
 

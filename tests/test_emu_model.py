@@ -100,6 +100,32 @@ def test_sharded_codec_over_gloo_with_the_real_kernels_under_the_cpu_model(model
     assert r.returncode == 0 and "7 passed" in r.stdout, (r.stdout + r.stderr)[-4000:]
 
 
+def test_bench_py_rehearsal_two_ranks_with_an_injected_failure(model_so):
+    # bench.py under torchrun, 2 ranks (gloo; the library's communicator over the NCCL model), sizes shrunk 512 x.  Rank 1's
+    # first round trip of the strong-scaling config raises after its collective (what happened on the 8-GPU box): both ranks
+    # must drop that config together, run the next one, and rank 0 must still print the one JSON line
+    import json
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    env = dict(os.environ, HB_EMU="1", HUFFB200_SO=model_so, HB_EMU_WORKERS="3", HB_DRYRUN_FAIL="1:4194304")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "emu", "bench_dryrun.py"),
+                        "--gpus", "2", "--size", str(2 << 20), "--steps", "3", "--shrink", "9"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=2400)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["sharded_parity"].endswith(": ok") and "aborted" not in d
+    cfgs = d["configs"]
+    assert [("error" in c) for c in cfgs] == [False, False, True, False], cfgs
+    assert "strong" in cfgs[2]["config"] and cfgs[2]["scaling"] == "strong"
+    assert cfgs[3]["decoder"] == "fused one-pass" and "general_frac" in d
+
+
 def test_cpp_mirror_of_the_reference_tests_under_the_cpu_model(model_so, tmp_path):
     # include/huff_coding.hpp (the C++ mirror of the reference API) with the reference's own test cases, linked against the model
     exe = str(tmp_path / "test_huff_coding_model")

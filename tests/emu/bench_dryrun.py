@@ -78,17 +78,23 @@ def _codec_event(self):
 
 sharded_mod.ShardedCodec._event = _codec_event
 
-# fault injection (tests of bench.py's containment): HB_DRYRUN_FAIL="<rank>:<letters>" makes that rank's first round trip over
-# an input of that many letters raise AFTER its collective, like a status returned by the decoder
+# fault injection (tests of bench.py's containment): HB_DRYRUN_FAIL="<rank>:<letters>[:before]" makes that rank's first round
+# trip over an input of that many letters raise AFTER its collective, like a status returned by the decoder -- or, with
+# ":before", before it, which leaves the other ranks waiting in a collective nobody will complete
 _fail = os.environ.get("HB_DRYRUN_FAIL")
 if _fail:
-    _fail_rank, _fail_size = (int(x) for x in _fail.split(":"))
+    _fail_rank, _fail_size = (int(x) for x in _fail.split(":")[:2])
+    _fail_before = _fail.endswith(":before")     # raise BEFORE the collective: the other ranks are left waiting (watchdog)
     _real_round_trip = sharded_mod.ShardedCodec.round_trip
     _fired = []
 
     def _round_trip(self, data, comp_buf, out_buf, want_events=False):
+        hit = self.rank == _fail_rank and data.numel() == _fail_size and not _fired
+        if hit and _fail_before:
+            _fired.append(1)
+            raise RuntimeError("libhuffb200: CUDA error [injected before the collective]")
         r = _real_round_trip(self, data, comp_buf, out_buf, want_events)
-        if self.rank == _fail_rank and data.numel() == _fail_size and not _fired:
+        if hit:
             _fired.append(1)
             raise RuntimeError("libhuffb200: buffer too small (status 5) [injected]")
         return r

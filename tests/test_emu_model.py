@@ -126,6 +126,23 @@ def test_bench_py_rehearsal_two_ranks_with_an_injected_failure(model_so):
     assert cfgs[3]["decoder"] == "fused one-pass" and "general_frac" in d
 
 
+def test_device_api_stays_inside_its_buffers_guard_pages(model_so):
+    # every buffer ends where include/huffb200.h says the library may stop, followed by a PROT_NONE page: a byte too far
+    # is a SIGSEGV (what compute-sanitizer would report on the GPU; the pool does not offer it)
+    env = dict(os.environ, HB_EMU="1", HUFFB200_SO=model_so)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "guard_check.py")], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and "guard pages: ok" in r.stdout, (r.returncode, (r.stdout + r.stderr)[-3000:])
+    # negative control: a size that runs 16 bytes into the guard page must kill the process
+    neg = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+           "import guard_check as g\nfrom tests.emu.model_engine import ModelEngine\nfrom huff_encoding_b200 import _lib as L\n"
+           "eng = ModelEngine(); d = g.guarded(1 << 16, 1, 16)\n"
+           "L.load().hb_histogram_u8_dev(eng.ctx.handle, d.data_ptr(), d.numel() + 16, eng._hist.data_ptr())\nprint('not caught')\n"
+           % (ROOT, os.path.join(ROOT, "tests", "emu")))
+    r = subprocess.run([sys.executable, "-c", neg], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode < 0 and "not caught" not in r.stdout, (r.returncode, r.stdout, r.stderr[-500:])
+
+
 def test_cpp_mirror_of_the_reference_tests_under_the_cpu_model(model_so, tmp_path):
     # include/huff_coding.hpp (the C++ mirror of the reference API) with the reference's own test cases, linked against the model
     exe = str(tmp_path / "test_huff_coding_model")

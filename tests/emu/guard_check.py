@@ -92,12 +92,11 @@ if __name__ == "__main__":
     eng = ModelEngine()
     rng = np.random.default_rng(3)
     cases = []
-    for gen, n in (("zipf", 1 << 20), ("english", 3 * 33792 * 8 // 4 // 16 * 16), ("uniform", 1 << 18), ("zipf", 4096), ("english", 16),
-                   ("zipf", 2_000_000 // 16 * 16)):
+    for gen, n in (("zipf", 1 << 19), ("english", 3 * 33792 * 8 // 4 // 16 * 16), ("uniform", 1 << 17), ("zipf", 4096), ("english", 16)):
         cases.append((gen, getattr(G, gen)(n, seed=n)))
     w = G.fibonacci_weights(n_fib=24, n_ones=40)
     fib = G.from_weights_runs(w)
-    cases.append(("fibonacci", fib[: fib.size // 16 * 16][:3_000_000 // 16 * 16]))
+    cases.append(("fibonacci", fib[: fib.size // 16 * 16][:600_000 // 16 * 16]))
     cases.append(("two letters", rng.choice(np.array([65, 66], np.uint8), size=1 << 16)))
     paths = {}
     for name, data in cases:

@@ -28,13 +28,85 @@ def model_so():
     return emu_build.build()
 
 
-def _run(model_so, args, extra_env=None, timeout=3000):
-    env = dict(os.environ, HB_EMU="1", HUFFB200_SO=model_so)
-    env.update(extra_env or {})
+class _Result:
+    def __init__(self, returncode, stdout, stderr):
+        self.returncode, self.stdout, self.stderr = returncode, stdout, stderr
+
+
+class _Jobs:
+    """The model runs are independent subprocesses: they all start at once (the machine has the cores) and every test
+    collects the result of its own."""
+
+    def __init__(self, model_so):
+        self.model_so, self.procs, self.done = model_so, {}, {}
+        import tempfile
+        self.tmp = tempfile.mkdtemp(prefix="hb_emu_jobs_")
+
+    def start(self, name, cmd, extra_env=None):
+        env = dict(os.environ, HB_EMU="1", HUFFB200_SO=self.model_so)
+        env.update(extra_env or {})
+        out = open(os.path.join(self.tmp, name + ".out"), "w+")
+        err = open(os.path.join(self.tmp, name + ".err"), "w+")
+        self.procs[name] = (subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=out, stderr=err, text=True), out, err)
+
+    def result(self, name, timeout=3000):
+        if name not in self.done:
+            p, out, err = self.procs[name]
+            try:
+                p.wait(timeout=timeout)
+            except subprocess.TimeoutExpired:
+                p.kill()
+                p.wait()
+            out.seek(0)
+            err.seek(0)
+            self.done[name] = _Result(p.returncode, out.read(), err.read())
+            out.close()
+            err.close()
+        return self.done[name]
+
+    def close(self):
+        for name, (p, out, err) in self.procs.items():
+            if p.poll() is None:
+                p.kill()
+
+
+def _pytest_cmd(args):
     cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + args
     for d in DESELECT:
         cmd += ["--deselect", d]
-    return subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+    return cmd
+
+
+def _free_port():
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+@pytest.fixture(scope="module")
+def jobs(model_so):
+    j = _Jobs(model_so)
+    emu = os.path.join(ROOT, "tests", "emu")
+    j.start("suites", _pytest_cmd(SUITES + ["-n", "4"]), {"HB_EMU_WORKERS": "2"})
+    j.start("single_rank", _pytest_cmd(["tests/test_gpu_multi.py", "-k", "single_rank"]))
+    j.start("eight_ranks", [sys.executable, os.path.join(emu, "multirank_check.py"), "8"])
+    j.start("bench_n1", [sys.executable, os.path.join(emu, "bench_dryrun.py"), "--size", str(4 << 20), "--steps", "4",
+                         "--shrink", "8"])
+    j.start("bench_n2", [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                         "127.0.0.1", "--master-port", str(_free_port()), os.path.join(emu, "bench_dryrun.py"),
+                         "--gpus", "2", "--size", str(2 << 20), "--steps", "3", "--shrink", "9"],
+            {"HB_EMU_WORKERS": "3", "HB_DRYRUN_FAIL": "1:4194304"})
+    j.start("gloo", [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "tests/test_sharded_gloo.py"],
+            {"HB_EMU_WORKERS": "2"})
+    j.start("guard", [sys.executable, os.path.join(emu, "guard_check.py")])
+    j.start("few_sms", _pytest_cmd(["tests/test_gpu_fused.py", "-k",
+                                    "fused_path_is_taken or matches_two_pass or wide_table or unaligned"]),
+            {"HB_EMU_SMS": "3", "HB_EMU_WORKERS": "1", "HB_EMU_ORDER": "down", "HB_EMU_BULK": "lazy"})
+    yield j
+    j.close()
 
 
 def test_the_model_exports_the_whole_c_abi(model_so):
@@ -45,8 +117,8 @@ def test_the_model_exports_the_whole_c_abi(model_so):
         assert hasattr(lib, name), name
 
 
-def test_gpu_parity_suites_pass_under_the_cpu_model(model_so):
-    r = _run(model_so, SUITES + ["-n", "4"], {"HB_EMU_WORKERS": "2"})
+def test_gpu_parity_suites_pass_under_the_cpu_model(jobs):
+    r = jobs.result("suites")
     tail = (r.stdout + r.stderr)[-4000:]
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
@@ -54,28 +126,24 @@ def test_gpu_parity_suites_pass_under_the_cpu_model(model_so):
     assert "skipped" not in r.stdout.splitlines()[-1], tail          # nothing may be skipped silently
 
 
-def test_single_rank_communicator_under_the_cpu_model(model_so):
+def test_single_rank_communicator_under_the_cpu_model(jobs):
     # hb_comm_init(1 rank) + hb_compress_shard_dev / hb_decompress_shard_dev (no NCCL involved with one rank)
-    r = _run(model_so, ["tests/test_gpu_multi.py", "-k", "single_rank"])
+    r = jobs.result("single_rank")
     assert r.returncode == 0 and "1 passed" in r.stdout, (r.stdout + r.stderr)[-4000:]
 
 
-def test_eight_ranks_inside_the_library_under_the_cpu_model(model_so):
+def test_eight_ranks_inside_the_library_under_the_cpu_model(jobs):
     # hb_comm_init + hb_compress_shard_dev (all-gather of the shard histograms) + hb_decompress_shard_dev with 8 ranks as
     # threads: concatenated shard streams == the oracle's stream of the concatenated input
-    env = dict(os.environ, HB_EMU="1", HUFFB200_SO=model_so)
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "multirank_check.py"), "8"], cwd=ROOT, env=env,
-                       capture_output=True, text=True, timeout=1500)
+    r = jobs.result("eight_ranks")
     assert r.returncode == 0 and r.stdout.count("ok:") == 3, (r.stdout + r.stderr)[-4000:]
 
 
-def test_bench_py_rehearsal_prints_one_json_line_with_every_key(model_so):
+def test_bench_py_rehearsal_prints_one_json_line_with_every_key(jobs):
     # bench.py from argument parsing to its JSON line (N = 1), library = CPU model, sizes shrunk 256 x: a rehearsal of the
     # control flow the driver runs at round end -- no number in that line means anything
     import json
-    env = dict(os.environ, HB_EMU="1", HUFFB200_SO=model_so)
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "bench_dryrun.py"), "--size", str(4 << 20),
-                        "--steps", "4", "--shrink", "8"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    r = jobs.result("bench_n1")
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, lines
@@ -90,31 +158,20 @@ def test_bench_py_rehearsal_prints_one_json_line_with_every_key(model_so):
     assert "e2e" in d["configs"][0]
 
 
-def test_sharded_codec_over_gloo_with_the_real_kernels_under_the_cpu_model(model_so):
+def test_sharded_codec_over_gloo_with_the_real_kernels_under_the_cpu_model(jobs):
     # tests/test_sharded_gloo.py (2-4 processes, gloo) with the model engine instead of the oracle-backed one: the Python
     # orchestration (all-gather of histograms, shard plan, start-bit encode, byte-sharded speculative decode with the
     # neighbour check) over the library's own kernels
-    env = dict(os.environ, HB_EMU="1", HUFFB200_SO=model_so, HB_EMU_WORKERS="2")
-    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "tests/test_sharded_gloo.py"], cwd=ROOT,
-                       env=env, capture_output=True, text=True, timeout=2400)
+    r = jobs.result("gloo")
     assert r.returncode == 0 and "7 passed" in r.stdout, (r.stdout + r.stderr)[-4000:]
 
 
-def test_bench_py_rehearsal_two_ranks_with_an_injected_failure(model_so):
+def test_bench_py_rehearsal_two_ranks_with_an_injected_failure(jobs):
     # bench.py under torchrun, 2 ranks (gloo; the library's communicator over the NCCL model), sizes shrunk 512 x.  Rank 1's
     # first round trip of the strong-scaling config raises after its collective (what happened on the 8-GPU box): both ranks
     # must drop that config together, run the next one, and rank 0 must still print the one JSON line
     import json
-    import socket
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    env = dict(os.environ, HB_EMU="1", HUFFB200_SO=model_so, HB_EMU_WORKERS="3", HB_DRYRUN_FAIL="1:4194304")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-                        "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "emu", "bench_dryrun.py"),
-                        "--gpus", "2", "--size", str(2 << 20), "--steps", "3", "--shrink", "9"],
-                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=2400)
+    r = jobs.result("bench_n2")
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]
     assert len(lines) == 1, r.stdout[-2000:]
@@ -126,12 +183,11 @@ def test_bench_py_rehearsal_two_ranks_with_an_injected_failure(model_so):
     assert cfgs[3]["decoder"] == "fused one-pass" and "general_frac" in d
 
 
-def test_device_api_stays_inside_its_buffers_guard_pages(model_so):
+def test_device_api_stays_inside_its_buffers_guard_pages(jobs, model_so):
     # every buffer ends where include/huffb200.h says the library may stop, followed by a PROT_NONE page: a byte too far
     # is a SIGSEGV (what compute-sanitizer would report on the GPU; the pool does not offer it)
     env = dict(os.environ, HB_EMU="1", HUFFB200_SO=model_so)
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "guard_check.py")], cwd=ROOT, env=env,
-                       capture_output=True, text=True, timeout=1500)
+    r = jobs.result("guard")
     assert r.returncode == 0 and "guard pages: ok" in r.stdout, (r.returncode, (r.stdout + r.stderr)[-3000:])
     # negative control: a size that runs 16 bytes into the guard page must kill the process
     neg = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
@@ -153,12 +209,11 @@ def test_cpp_mirror_of_the_reference_tests_under_the_cpu_model(model_so, tmp_pat
     assert r.returncode == 0, r.stdout + r.stderr
 
 
-def test_decoder_tests_with_few_sms_and_one_resident_cta(model_so):
+def test_decoder_tests_with_few_sms_and_one_resident_cta(jobs):
     # other interleavings: 3 SMs, CTAs strictly one after the other, and the threads of a CTA taking their turns in
     # DESCENDING order (code that leans on the ascending order -- a missing barrier or __syncwarp -- gives other results),
     # bulk copies landing only when their mbarrier is waited on (a read of the window before the wait would see stale bytes)
-    r = _run(model_so, ["tests/test_gpu_fused.py", "-k", "fused_path_is_taken or matches_two_pass or wide_table or unaligned"],
-             {"HB_EMU_SMS": "3", "HB_EMU_WORKERS": "1", "HB_EMU_ORDER": "down", "HB_EMU_BULK": "lazy"})
+    r = jobs.result("few_sms")
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
 
 

@@ -477,3 +477,27 @@ def test_host_api_pipelined_fixed_length_decode_multi_chunk(hb):
         out = np.empty(n + 3, dtype=np.uint8)                      # caller-owned buffer variant
         back2 = hb.decompress(cd, out=out)
         assert back2.size == n and np.array_equal(back2, data)
+
+
+def test_n3_deepest_trees_hb_tree_can_hold(hb):
+    # right-leaning chains as try_from_bin may deliver them: 256 distinct leaves (codes of 1 .. 255 bits) and 257 leaves with
+    # one letter twice (the longest code hb_tree can hold: 256 bits).  Code words longer than a whole 1 024-bit subsequence's
+    # look-back, spanning many threads' subsequences
+    def chain_bits(letters):
+        return "".join("1" + "0" + format(l, "08b") for l in letters[:-1]) + "0" + format(letters[-1], "08b")
+
+    rng = np.random.default_rng(12)
+    for letters in (list(range(256)), list(range(256)) + [7]):
+        bits = chain_bits(letters)
+        raw = np.packbits(np.array([int(b) for b in bits], dtype=np.uint8))
+        tree = hb.HuffTree.try_from_bin(raw.tobytes(), len(bits))
+        otree = O.tree_from_bin(raw, len(bits))
+        assert tree.read_codes() == otree.codes()
+        assert tree.raw.max_len == len(letters) - 1
+        data = rng.integers(0, 256, size=30_000).astype(np.uint8)          # mean code length ~128 bits
+        data[::97] = 255                                                    # the deepest leaves, regularly
+        comp, pad = O.compress_with_tree(data, otree)
+        got = hb.decompress(hb.CompressData(comp, pad, tree))
+        assert np.array_equal(got, O.decompress(comp, pad, otree)), _first_diff(got, data)
+        # (with the duplicated letter the round trip still returns the letters: both leaves carry the same letter)
+        assert np.array_equal(got, data)

@@ -558,6 +558,14 @@ def run_ours(args):
             except ConfigFailed as e:                       # raised by every rank together: carry on with the next config
                 r["error"] = str(e)
                 sys.stderr.write(f"bench.py rank {rank}: config '{label}' failed: {e}\n")
+            try:                                            # measured DRAM bytes per launch, where an ncu capture of this shape exists
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                if f"{workload}:{nbytes}" in tj and "error" not in r:
+                    r["traffic_bytes_per_launch"] = tj[f"{workload}:{nbytes}"]
+                    r["algorithmic_bytes"] = {"hist": r["bytes_per_gpu"], "encode": r["bytes_per_gpu"] + r["comp_bytes_per_gpu"],
+                                              "decode": r["bytes_per_gpu"] + r["comp_bytes_per_gpu"]}
+            except Exception:
+                pass
             configs.append(r)
             if rank == 0 and "general_frac" not in line and "error" not in r and workload == "zipf" and nbytes == gib:
                 line["general_frac"] = {"encode": r["frac"]["encode"], "decode": r["frac"]["decode"],

@@ -294,7 +294,15 @@ def measure(codec, eng, datas, comp_buf, out_buf, steps, warmup, torch, dist, wo
     def checkpoint(what):
         tick()
         if not all_ranks_ok(not errors, torch, dist, dev):
-            raise ConfigFailed(f"{what}: " + (errors[0] if errors else "failed on another rank"))
+            msg = errors[0] if errors else None
+            if dist is not None:                                # every rank is here: tell all of them what happened where
+                try:
+                    msgs = [None] * world
+                    dist.all_gather_object(msgs, msg)
+                    msg = next((f"rank {r}: {m}" for r, m in enumerate(msgs) if m), msg)
+                except Exception:                              # noqa: BLE001 -- the message is a nicety, the agreement is not
+                    pass
+            raise ConfigFailed(f"{what}: " + (msg or "failed on another rank"))
 
     with torch.cuda.stream(stream):
         for i in range(warmup):

@@ -153,7 +153,7 @@ def test_an_error_on_one_rank_fails_the_config_on_every_rank_and_the_next_config
         p.join(timeout=60)
         assert p.exitcode == 0
     (r0, e0, n0, c0), (r1, e1, n1, c1) = got
-    assert "failed on another rank" in e0 and "buffer too small" in e1
+    assert e0 == e1 and "rank 1: RuntimeError" in e0 and "buffer too small" in e0      # every rank learns what failed where
     assert n0 == n1 == 100
     assert c0 == c1 == 6                 # both ranks kept the schedule up to the checkpoint: 2 warm-up + 4 timed trips
 

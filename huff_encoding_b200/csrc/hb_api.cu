@@ -1062,7 +1062,8 @@ hb_status hb_compress_shard_dev(hb_ctx *ctx, const uint8_t *d_data, size_t n, in
     layout->total_bits = total;
     layout->start_bit = static_cast<uint32_t>(offset % 8);
     layout->padding_bits = static_cast<uint8_t>((8 - total % 8) % 8);
-    layout->comp_len = static_cast<size_t>((layout->start_bit + layout->bits + 7) / 8);
+    // an empty shard owns no byte of the stream (not even the one its neighbours share)
+    layout->comp_len = layout->bits ? static_cast<size_t>((layout->start_bit + layout->bits + 7) / 8) : 0;
     if (((layout->comp_len + 3) & ~static_cast<size_t>(3)) > out_cap) return HB_ERR_CAPACITY;
     if (n == 0) return HB_OK;
     return launch_encode(ctx, d_data, n, tree_out, layout->start_bit, d_out, nullptr, true);

@@ -63,7 +63,7 @@ class ShardedCodec:
         offset = sum(all_bits[: self.rank])
         total = sum(all_bits)
         start_bit = offset % 8
-        comp_len = (start_bit + my_bits + 7) // 8
+        comp_len = (start_bit + my_bits + 7) // 8 if my_bits else 0       # an empty shard owns no byte of the stream
         if comp_buf.numel() < ((comp_len + 3) // 4) * 4:
             raise ValueError("comp_buf too small for this shard")
         if marks is not None:
@@ -164,7 +164,7 @@ class ShardedCodec:
         off = 0
         for g in range(self.world):
             sb = off % 8
-            ln = (sb + info["all_bits"][g] + 7) // 8
+            ln = (sb + info["all_bits"][g] + 7) // 8 if info["all_bits"][g] else 0
             piece = recv[g][:ln].cpu().numpy()
             out[off // 8: off // 8 + ln] |= piece             # the shared boundary byte is OR-merged
             off += info["all_bits"][g]

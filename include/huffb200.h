@@ -220,7 +220,7 @@ typedef struct hb_shard_layout {
     uint64_t bit_offset;     /* where this shard's first bit sits in the whole stream */
     uint64_t bits;           /* code bits of this shard */
     uint64_t total_bits;     /* code bits of all shards */
-    size_t   comp_len;       /* bytes of d_out in use: ceil((start_bit + bits) / 8) */
+    size_t   comp_len;       /* bytes of d_out in use: ceil((start_bit + bits) / 8); 0 for an empty shard (bits == 0) */
     uint32_t start_bit;      /* bit_offset % 8: the first start_bit bits of d_out[0] are zero (the neighbour's) */
     uint8_t  padding_bits;   /* of the whole stream (comp.rs:446) */
 } hb_shard_layout;

@@ -72,3 +72,7 @@ if __name__ == "__main__":
     run(world, "english", [base + 13 * r for r in range(world)])
     run(world, "zipf", [base // 2 + 4097 * r for r in range(world)])
     run(2, "uniform", [300_000, 300_000])                 # fixed-length fast path, byte-aligned shards
+    # empty and tiny shards: an empty shard owns no byte of the stream, not even the one its neighbours share
+    run(8, "english", [0, 1, 17, 0, 100_001, 3, 65_536, 1])
+    run(8, "zipf", [5, 0, 0, 0, 0, 0, 0, 300_001])
+    run(3, "zipf", [1, 1, 1])

@@ -136,7 +136,7 @@ def test_eight_ranks_inside_the_library_under_the_cpu_model(jobs):
     # hb_comm_init + hb_compress_shard_dev (all-gather of the shard histograms) + hb_decompress_shard_dev with 8 ranks as
     # threads: concatenated shard streams == the oracle's stream of the concatenated input
     r = jobs.result("eight_ranks")
-    assert r.returncode == 0 and r.stdout.count("ok:") == 3, (r.stdout + r.stderr)[-4000:]
+    assert r.returncode == 0 and r.stdout.count("ok:") == 6, (r.stdout + r.stderr)[-4000:]
 
 
 def test_bench_py_rehearsal_prints_one_json_line_with_every_key(jobs):

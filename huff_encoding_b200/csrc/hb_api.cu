@@ -445,8 +445,10 @@ hb_status run_count_pass(hb_ctx *ctx, const uint8_t *d_buf, uint64_t avail_bits,
     if (reinterpret_cast<uintptr_t>(d_buf) & 3) return HB_ERR_INVALID_ARG;
     if (own_end > avail_bits) own_end = avail_bits;
     if (own_begin >= own_end) {
+        // an empty range passes the chain through: with a known entry (the first code-word start at or after own_begin) that
+        // start is also the first one at or after own_end; without one there is nothing to report but the range itself
         info->entry_bit = entry_bit;
-        info->exit_bit = own_begin;
+        info->exit_bit = (entry_bit >= 0 && static_cast<uint64_t>(entry_bit) > own_begin) ? static_cast<uint64_t>(entry_bit) : own_begin;
         info->n_letters = 0;
         ctx->last_dec_total = 0;
         ctx->last_dec.n_blocks = 0;

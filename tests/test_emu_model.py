@@ -102,6 +102,7 @@ def jobs(model_so):
     j.start("gloo", [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "tests/test_sharded_gloo.py"],
             {"HB_EMU_WORKERS": "2"})
     j.start("guard", [sys.executable, os.path.join(emu, "guard_check.py")])
+    j.start("sharded_fuzz", [sys.executable, os.path.join(emu, "sharded_fuzz.py"), "30"], {"HB_EMU_WORKERS": "2"})
     j.start("few_sms", _pytest_cmd(["tests/test_gpu_fused.py", "-k",
                                     "fused_path_is_taken or matches_two_pass or wide_table or unaligned"]),
             {"HB_EMU_SMS": "3", "HB_EMU_WORKERS": "1", "HB_EMU_ORDER": "down", "HB_EMU_BULK": "lazy"})
@@ -163,7 +164,7 @@ def test_sharded_codec_over_gloo_with_the_real_kernels_under_the_cpu_model(jobs)
     # orchestration (all-gather of histograms, shard plan, start-bit encode, byte-sharded speculative decode with the
     # neighbour check) over the library's own kernels
     r = jobs.result("gloo")
-    assert r.returncode == 0 and "7 passed" in r.stdout, (r.stdout + r.stderr)[-4000:]
+    assert r.returncode == 0 and "10 passed" in r.stdout, (r.stdout + r.stderr)[-4000:]
 
 
 def test_bench_py_rehearsal_two_ranks_with_an_injected_failure(jobs):
@@ -197,6 +198,13 @@ def test_device_api_stays_inside_its_buffers_guard_pages(jobs, model_so):
            % (ROOT, os.path.join(ROOT, "tests", "emu")))
     r = subprocess.run([sys.executable, "-c", neg], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode < 0 and "not caught" not in r.stdout, (r.returncode, r.stdout, r.stderr[-500:])
+
+
+def test_sharded_codec_fuzz_with_thread_ranks_under_the_cpu_model(jobs):
+    # ShardedCodec (compress / gather_stream / shard decode / byte-sharded decode with the neighbour check) over the real
+    # kernels' code, 1..8 ranks as threads, shards from 0 letters up, streams down to a few bytes
+    r = jobs.result("sharded_fuzz")
+    assert r.returncode == 0 and "sharded fuzz: ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
 
 
 def test_cpp_mirror_of_the_reference_tests_under_the_cpu_model(model_so, tmp_path):

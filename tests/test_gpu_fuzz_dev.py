@@ -66,7 +66,11 @@ def test_fuzz_device_api(eng, seed):
         slack = int(rng.choice([0, 0, 1, 31, 64]))
         base = torch.full((n + 128 + slack,), 0xEE, dtype=torch.uint8, device=dev())
         out = base[off: off + n + slack]
-        e, x, cnt = eng.decode_shard(buf, sb + bits, sb, sb + bits, int(rng.integers(0, 1 << 20)) * 8, tree, sb, out)
+        # stream_bit0 = position of buffer bit 0 in the "whole stream": the shard starts at buffer bit sb, so it must be
+        # congruent to -sb modulo the gcd of the code lengths (the phase of the speculative entries)
+        g = max(int(tree.raw.len_gcd), 1)
+        stream_bit0 = g * int(rng.integers(64, 1 << 20)) - sb
+        e, x, cnt = eng.decode_shard(buf, sb + bits, sb, sb + bits, stream_bit0, tree, sb, out)
         dev_sync()
         assert cnt == n and e == sb, tag + f" decode_shard sb={sb} off={off} slack={slack}"
         assert np.array_equal(out[:n].cpu().numpy(), data), tag + f" decode_shard sb={sb} off={off} slack={slack}"
@@ -78,14 +82,14 @@ def test_fuzz_device_api(eng, seed):
             lens = np.array([tree.raw.code_len[b] for b in range(256)], dtype=np.int64)[data]
             starts = np.concatenate([[0], np.cumsum(lens)]) + sb
             cut = sb + int(rng.integers(1, bits))
-            eL, xL, cL = eng.decode_count(buf, sb + bits, sb, cut, 0, tree, entry_bit=sb)
+            eL, xL, cL = eng.decode_count(buf, sb + bits, sb, cut, g * 64 - sb, tree, entry_bit=sb)
             first_right = int(np.searchsorted(starts[:-1], cut, side="left"))
             assert cL == first_right and xL == (starts[first_right] if first_right < n else sb + bits), tag + f" cut={cut}"
             left = torch.empty(cL + 32, dtype=torch.uint8, device=dev())
             eng.decode_write(left)
-            eR, xR, cR = eng.decode_count(buf, sb + bits, cut, sb + bits, 0, tree, entry_bit=-1)
+            eR, xR, cR = eng.decode_count(buf, sb + bits, cut, sb + bits, g * 64 - sb, tree, entry_bit=-1)
             if eR != xL:                                        # speculation refuted by the neighbour: redo with the truth
-                eR, xR, cR = eng.decode_count(buf, sb + bits, cut, sb + bits, 0, tree, entry_bit=xL)
+                eR, xR, cR = eng.decode_count(buf, sb + bits, cut, sb + bits, g * 64 - sb, tree, entry_bit=xL)
             right = torch.empty(cR + 32, dtype=torch.uint8, device=dev())
             eng.decode_write(right)
             dev_sync()

@@ -160,7 +160,7 @@ def _worker(rank, world, port, kind, n_total, q):
 
 CASES = [(2, "english", 60_001), (2, "zipf", 50_003), (3, "uniform", 30_000), (2, "uniform", 4096)]
 if os.environ.get("HB_EMU") == "1":          # real kernels (CPU model): sizes that span many chunks and sub-regions
-    CASES += [(2, "zipf", 3_000_001), (3, "english", 2_000_003), (4, "zipf", 1_234_567),
+    CASES += [(2, "zipf", 3_000_001), (4, "english", 1_234_567),
               (3, "english", 2), (4, "zipf", 5), (4, "english", 40)]        # empty and few-letter shards
 
 

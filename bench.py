@@ -5,13 +5,17 @@
                     [--size BYTES]
 
 One "step" = one pass of the hot path over one batch of synthetic input resident in HBM:
-    compress   = histogram kernel -> (N>1: allreduce of the 256 bins) -> host tree -> encode kernel
-    decompress = count pass -> (N>1: neighbour entry check) -> write pass
-At N=1 the workload is BASELINE.json configs[1] (1 GiB uniform random bytes).  At N>1 every rank holds one 1 GiB
-contiguous shard of an N GiB input (weak scaling); shards exchange only the 2 KiB histogram and 8-byte bit totals.
+    compress   = histogram kernel -> (N>1: all-gather of the G shard histograms inside the library) -> host tree -> encode kernel
+    decompress = the one-pass fused decoder (or, by tree: fixed-length translation / the two-pass count + write kernels)
+At N=1 the workload is BASELINE.json configs[1] (1 GiB uniform random bytes), two inputs rotated step by step so that every
+step meets a tree the context did not see in the previous one.  At N>1 every rank holds one 1 GiB contiguous shard of an
+N GiB input (weak scaling); shards exchange only the 2 KiB histograms.
 `value` = input bytes of all ranks / max-over-ranks device time of the K steps (round trip: compress + decompress).
-`e2e`   = the same round trip through the host-buffer C ABI (hb_compress_u8 / hb_decompress_u8) with pinned HOST
+`e2e`   = the same round trip through the host-buffer C ABI (hb_compress_u8_into / hb_decompress_u8_into) with pinned HOST
           buffers, host<->device copies inside the timed region.
+`configs` = the other BASELINE shapes on the same GPUs (Zipf 1 GiB / 4 GiB weak + strong, text, Fibonacci, Zipf(1.5)): the
+          variable-length kernels; a failure there is contained (all ranks skip the config together) and a stalled run
+          prints the line it has (Watchdog).
 The oracle (oracle/) is executed only for `cpu_baseline` and for `--impl reference`; never on the measured GPU path.
 """
 from __future__ import annotations
